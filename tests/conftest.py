@@ -1,0 +1,26 @@
+import os
+import sys
+import tempfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# the reference's hooker constructor mkdir's <cache>/daam/heads (daam/trace.py:211-217): keep that out of $HOME
+os.environ.setdefault('XDG_CACHE_HOME', tempfile.mkdtemp(prefix='daam_cache_'))
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason='no CUDA device')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
