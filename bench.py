@@ -1,0 +1,463 @@
+#!/usr/bin/env python
+"""Benchmark of the cross-attention heat-map hot path (BASELINE.json metric: heat-map px/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload sd21|sdxl] [--prompts P]
+
+Workload (BASELINE.json configs[1]): random-init SD-2.1-base UNet shapes, 64x64 latent, 77 tokens, bf16, the 15 traced
+cross-attention layers of one denoising step. A bench "step" is one pass of the hot path over one step's Q/K:
+13.80 M accumulated heat-map px (sum over traced layers of heads*77*h*w).
+
+One JSON line is printed by rank 0:
+  value         px/s with Q/K already resident in HBM: one persistent `daam_accumulate` launch per step (all 15
+                layers), K steps timed with CUDA events between barriers, max over ranks, x N ranks (weak scaling).
+                Inputs exceed L2: the steps rotate over R independent resident prompt sets (accumulators + Q/K).
+  roofline      the accumulate kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json), algorithmic bytes.
+  e2e           the same metric through the public API -- `with trace(pipe): pipe(prompt, K steps);
+                compute_global_heat_map()` on the cross-attention skeleton of the UNet -- with the pipeline inputs in
+                pinned HOST memory copied H2D every step and results read D2H inside the timed region.
+  cpu_baseline  the oracle's port of the reference hot path (rows a3+a4+a6) timed on this box's host cores on a bounded
+                sample of the same Q/K shapes.
+  hook_overhead hooked vs un-hooked forward of a full-cost synthetic UNet (resnets, self-attention, feed-forward), ms/step.
+
+`--impl reference` times the reference's own CPU implementation of the path instead (the oracle's op-for-op port of
+daam/trace.py's hook, since the Python reference cannot travel to the GPU box) through the same pipeline API on CPU.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'heatmap px/s (layers x steps x tokens)'
+UNIT = 'px/s'
+TOKENS = 77
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# workload description
+# --------------------------------------------------------------------------------------------------------------------
+def traced_layers(workload: str):
+    """(hw, heads) of every traced layer in the reference's layer_idx order, head_dim 64."""
+    if workload == 'sd21':
+        return [(256, 20)] * 3 + [(1024, 10)] * 3 + [(4096, 5)] * 3 + [(4096, 5)] * 2 + [(1024, 10)] * 2 + [(256, 20)] * 2
+    if workload == 'sdxl':   # 60 layers (default trace, no mid block): up 3x10 @32^2, 3x2 @64^2; down 2x2 @64^2, 2x10 @32^2
+        return [(1024, 20)] * 30 + [(4096, 10)] * 6 + [(4096, 10)] * 4 + [(1024, 20)] * 20
+    raise ValueError(workload)
+
+
+def px_per_step(layers, n_prompts=1):
+    return n_prompts * sum(h * TOKENS * hw for hw, h in layers)
+
+
+def literal_px_per_step(layers, n_prompts=1, x=64):
+    return n_prompts * len(layers) * TOKENS * x * x      # BASELINE-literal "layers x tokens x 64^2"
+
+
+def algorithmic_bytes_per_step(layers, n_prompts=1, esize=2, d=64):
+    """Q + K in the config dtype, fp32 accumulator read + write (conditional half only)."""
+    return n_prompts * sum(h * hw * d * esize + h * TOKENS * d * esize + h * TOKENS * hw * 4 * 2 for hw, h in layers)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def recorded_traffic(workload):
+    """dram bytes per launch of the accumulate kernel from the committed ncu capture, if there is one."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'accumulate_traffic.json')) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, during the timed regions)
+# --------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={self.FIELDS}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'note': 'nvidia-smi unavailable'}
+        time.sleep(0.15)
+        self.proc.terminate()
+        inside = [r for t, r in self.rows if any(a <= t <= b for a, b in windows)] or [r for _, r in self.rows]
+        sm = sorted(float(r[0]) for r in inside if r[0].replace('.', '').isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in inside for n, v in zip(names, r[4:8]) if v.lower().startswith('active')})
+        mx = [float(r[1]) for r in inside if r[1].replace('.', '').isdigit()]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(inside)}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# distributed helpers
+# --------------------------------------------------------------------------------------------------------------------
+class Dist:
+    def __init__(self, n_gpus: int):
+        import torch.distributed as dist
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        self.dist = dist
+        if self.world > 1:
+            os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group('nccl', device_id=torch.device('cuda', self.local_rank))
+        else:
+            torch.cuda.set_device(0)
+        if n_gpus != self.world:
+            log(f'[bench] --gpus {n_gpus} but WORLD_SIZE {self.world}: launch with torchrun for N > 1; using {self.world}')
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def max_ms(self, ms: float) -> float:
+        if self.world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# legs
+# --------------------------------------------------------------------------------------------------------------------
+def build_sets(layers, n_prompts, dtype, n_sets, seed):
+    """R independent resident prompt sets: per layer Q [2P, hw, H*64], K [2P, 77, H*64] and the fp32 accumulators."""
+    from daam_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    sets = []
+    for _ in range(n_sets):
+        descs, keep = [], []
+        for hw, heads in layers:
+            q = torch.randn(2 * n_prompts, hw, heads * 64, generator=g, device='cuda', dtype=torch.float32).to(dtype)
+            k = torch.randn(2 * n_prompts, TOKENS, heads * 64, generator=g, device='cuda', dtype=torch.float32).to(dtype)
+            acc = ops.new_accumulator(n_prompts, heads, hw, 'cuda')
+            descs.append(ops.make_layer_desc(q, k, acc, heads, 0.125))
+            keep.append((q, k, acc))
+        sets.append((descs, keep))
+    return sets
+
+
+def leg_value(args, layers, dtype, D: Dist, windows):
+    from daam_b200 import _native, ops
+    set_bytes = algorithmic_bytes_per_step(layers, args.prompts) - px_per_step(layers, args.prompts) * 4  # acc counted once
+    n_sets = max(2, -(-int(320e6) // max(1, set_bytes)))      # working set >= 320 MB > 126 MB L2
+    sets = build_sets(layers, args.prompts, dtype, n_sets, 1234 + D.rank)
+    stream = torch.cuda.current_stream()
+    for i in range(args.warmup):
+        ops.accumulate(sets[i % n_sets][0], 'cuda', stream)
+    torch.cuda.synchronize()
+    D.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _native.launch_count()
+    t0 = time.time()
+    e0.record(stream)
+    for i in range(args.steps):
+        ops.accumulate(sets[i % n_sets][0], 'cuda', stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    D.barrier()
+    torch.cuda.synchronize()
+    windows.append((t0, time.time()))
+    ms = D.max_ms(e0.elapsed_time(e1))
+    launches = _native.launch_count() - launches0
+    # sanity: the timed work really accumulated (softmax rows sum to 1 -> each head gained hw per visit)
+    q, k, acc = sets[0][1][0]
+    visits = len(range(0, args.warmup, n_sets)) + len(range(0, args.steps, n_sets))
+    got = float(acc[0, 0].double().sum())
+    assert abs(got - visits * acc.shape[-1]) < 1e-3 * got, (got, visits)
+    return ms, launches, n_sets
+
+
+def leg_e2e(args, spec, dtype, D: Dist, windows):
+    """Public API on the cross-attention skeleton: host-resident pipeline inputs, H2D/D2H every step."""
+    from daam_b200 import trace
+    from daam_b200.distributed import gather_heat_maps
+    from daam_b200.synthetic import make_pipeline
+    pipe = make_pipeline(spec, body='skeleton', dtype=dtype, device='cuda', seed=D.rank, init_on_device=True)
+    prompts = ['a photo of a dog chasing a red ball on the beach at sunset'] * args.prompts
+    prompt_arg = prompts[0] if args.prompts == 1 else prompts
+    out_h = None
+    with trace(pipe, batch_prompts=args.prompts > 1) as tc:
+        pipe(prompt_arg, num_inference_steps=max(1, args.warmup))
+        tc.compute_global_heat_map()
+        torch.cuda.synchronize()
+        D.barrier()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pipe(prompt_arg, num_inference_steps=args.steps)
+        maps = [tc.compute_global_heat_map(prompt_idx=i).heat_maps for i in range(args.prompts)]
+        if D.world > 1:   # the one optional collective: finished maps to every rank (1.26 MB per prompt)
+            allmaps = gather_heat_maps(maps, args.prompts * D.world, maps[0].shape[-1])
+        else:
+            allmaps = torch.stack([m for m in maps])
+        out_h = allmaps.to('cpu', non_blocking=False)          # D2H of the result
+        e1.record()
+        torch.cuda.synchronize()
+        D.barrier()
+        torch.cuda.synchronize()
+        windows.append((t0, time.time()))
+    ms = D.max_ms(e0.elapsed_time(e1))
+    h2d = pipe.h2d_bytes_per_step
+    d2h = pipe.d2h_bytes_per_step + out_h.numel() * 4 / max(1, args.steps) / max(1, D.world)
+    assert torch.isfinite(out_h).all() and float(out_h.sum()) > 0
+    return ms, h2d, d2h
+
+
+def leg_hook_overhead(args, spec, dtype, windows):
+    """Hooked vs un-hooked forward of the full-cost synthetic UNet, CUDA-event timed, median over steps."""
+    from daam_b200 import trace
+    from daam_b200.synthetic import make_pipeline
+    pipe = make_pipeline(spec, body='full', dtype=dtype, device='cuda', seed=0, init_on_device=True)
+    n = 20
+    spec_ = pipe.unet.spec
+    lat = torch.randn(2, spec_.in_channels, spec_.sample_size, spec_.sample_size, device='cuda', dtype=dtype)
+    emb = torch.randn(2, spec_.tokens, spec_.cross_attention_dim, device='cuda', dtype=dtype)
+
+    def run(k):
+        times = []
+        for i in range(k):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            pipe.unet(lat, 500.0, emb)
+            b.record()
+            times.append((a, b))
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in times)
+        return ts[len(ts) // 2]
+
+    t0 = time.time()
+    with torch.no_grad():
+        run(5)
+        base = run(n)
+        res = {}
+        for mode in ('step', 'layer'):
+            with trace(pipe, launch=mode) as tc:
+                run(5)
+                res[mode] = run(n)
+                tc.synchronize()
+        base2 = run(n)
+    windows.append((t0, time.time()))
+    base = min(base, base2)
+    return {'unhooked_ms_per_step': round(base, 4),
+            'hooked_ms_per_step': round(res['step'], 4), 'overhead_ms_per_step': round(res['step'] - base, 4),
+            'overhead_pct': round(100 * (res['step'] - base) / base, 3),
+            'hooked_layer_mode_ms_per_step': round(res['layer'], 4),
+            'model': f'{spec.name} full-body synthetic UNet, CFG batch 2, {str(dtype).split(".")[-1]}, median of {n} forwards'}
+
+
+def leg_cpu_baseline(layers, budget_s=12.0):
+    """Oracle port of the hot-path stages on the host cores: baddbmm+softmax (a3), unravel (a4), per-head update (a6)."""
+    from oracle import daam_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    qs = [torch.randn(2, hw, h * 64, generator=g) for hw, h in layers]
+    ks = [torch.randn(2, TOKENS, h * 64, generator=g) for hw, h in layers]
+    store = O.OracleHeatMaps()
+
+    def one_step():
+        for i, ((hw, h), q, k) in enumerate(zip(layers, qs, ks)):
+            maps = O.port_layer_step(q, k, h, 0.125)
+            for head, m in enumerate(maps):
+                store.update(1, i, head, m)
+
+    one_step()
+    t0, n = time.time(), 0
+    while True:
+        one_step()
+        n += 1
+        if time.time() - t0 > budget_s or n >= 16:
+            break
+    dt = time.time() - t0
+    return {'value': px_per_step(layers) * n / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{n} steps x {len(layers)} layers of the same Q/K shapes, fp32 (reference CPU dtype), '
+                      f'stages a3+a4+a6 (oracle/daam_oracle.py port_layer_step + update), {dt:.1f} s'}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# reference arm
+# --------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU hook path (op-for-op port; `oracle/` is the only thing executed) through the pipeline API."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from daam_b200.synthetic import SD21_SPEC, SDXL_SPEC, make_pipeline
+    from oracle import daam_oracle as O
+    spec = SD21_SPEC if args.workload == 'sd21' else SDXL_SPEC
+    layers = traced_layers(args.workload)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pipe = make_pipeline(spec, body='skeleton', dtype=torch.float32, device='cpu', seed=0)
+    prompt = 'a photo of a dog chasing a red ball on the beach at sunset'
+    budget = 150.0
+    with torch.no_grad(), O.OracleTrace(pipe) as ot:
+        t = time.time()
+        pipe(prompt, num_inference_steps=1)
+        ot.compute_global_heat_map()
+        step_cost = time.time() - t
+        warm = min(args.warmup, max(0, int(20.0 / step_cost) - 1))
+        if warm:
+            pipe(prompt, num_inference_steps=warm)
+        steps = max(1, min(args.steps, int(budget / step_cost)))
+        t0 = time.time()
+        pipe(prompt, num_inference_steps=steps)
+        t_steps = time.time() - t0
+        ot.compute_global_heat_map()
+        dt = time.time() - t0
+    ms = dt / steps * 1e3
+    value = px_per_step(layers) * steps / dt
+    sample = (f'{steps} of the requested {args.steps} steps (bounded to ~{budget:.0f} s; the path has no step-dependent '
+              f'cost) of the {spec.name} cross-attention skeleton on CPU fp32 through OracleTrace (port of '
+              f'daam/trace.py hooks), + one compute_global_heat_map; hooked forward {t_steps / steps * 1e3:.0f} ms/step')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(args), 'px_per_step': px_per_step(layers), 'steps_timed': steps},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    base = {'sd21': 'random-init SD-2.1-base UNet shapes, 64x64 latent, 77 tokens, 15 traced cross-attn layers/step',
+            'sdxl': 'random-init SDXL UNet shapes, 128x128 latent, 77 tokens, 60 traced cross-attn layers/step'}
+    return f'{base[args.workload]}, {args.prompts} prompt(s)/GPU, {args.dtype}'
+
+
+# --------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)       # BASELINE configs[1]: 50 denoising steps
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='daam_b200', choices=['daam_b200', 'reference'])
+    ap.add_argument('--workload', default='sd21', choices=['sd21', 'sdxl'])
+    ap.add_argument('--prompts', type=int, default=1, help='prompts per GPU traced together (batch_prompts mode)')
+    ap.add_argument('--dtype', default=None, choices=['bf16', 'fp16', 'fp32'])
+    ap.add_argument('--skip-overhead', action='store_true')
+    ap.add_argument('--skip-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.dtype is None:
+        args.dtype = 'bf16' if args.workload == 'sd21' else 'fp16'
+    args.warmup = max(3, args.warmup)
+
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+
+    from daam_b200 import _native
+    from daam_b200.synthetic import SD21_SPEC, SDXL_SPEC
+    dtype = {'bf16': torch.bfloat16, 'fp16': torch.float16, 'fp32': torch.float32}[args.dtype]
+    spec = SD21_SPEC if args.workload == 'sd21' else SDXL_SPEC
+    layers = traced_layers(args.workload)
+    D = Dist(args.gpus)
+    _native.load()
+    sampler = ClockSampler(D.local_rank) if D.rank == 0 else None
+    windows = []
+
+    with torch.no_grad():
+        ms, launches, n_sets = leg_value(args, layers, dtype, D, windows)
+        e2e_ms, h2d, d2h = leg_e2e(args, spec, dtype, D, windows)
+        overhead = None
+        if not args.skip_overhead and D.rank == 0 and D.world == 1:
+            try:
+                overhead = leg_hook_overhead(args, spec, dtype, windows)
+            except Exception as e:   # reported, never silently dropped
+                overhead = {'error': repr(e)}
+    D.barrier()
+    if D.rank != 0:
+        D.close()
+        return
+    clocks = sampler.stop(windows)
+    cpu = None
+    if not args.skip_cpu and D.world == 1:
+        cpu = leg_cpu_baseline(layers)
+
+    n = D.world
+    px = px_per_step(layers, args.prompts)
+    esize = 4 if args.dtype == 'fp32' else 2
+    bytes_step = algorithmic_bytes_per_step(layers, args.prompts, esize)
+    peak, peak_src = measured_peak()
+    achieved = bytes_step / (ms / args.steps * 1e-3) / 1e9        # GB/s per GPU (per-rank launch duration, max over ranks)
+    line = {
+        'metric': METRIC, 'value': px * args.steps * n / (ms * 1e-3), 'unit': UNIT, 'n_gpus': n, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+        'config': {
+            'workload': workload_name(args), 'px_per_step': px, 'px_definition': 'sum over traced layers of heads*77*h*w',
+            'literal_px_per_step': literal_px_per_step(layers, args.prompts),
+            'l2': f'inputs larger than L2: steps rotate over {n_sets} resident prompt sets '
+                  f'({n_sets * (bytes_step - px * 4) / 1e6:.0f} MB of accumulators+Q/K vs 126 MB L2), no flush',
+            'launch': 'one persistent kernel per step covering all traced layers', 'parallelism': f'prompts sharded, dp{n}',
+        },
+        'clocks': clocks,
+        'e2e': {'value': px * args.steps * n / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps,
+                'what': 'with trace(pipe): pipe(prompt, K steps) on the cross-attn skeleton UNet (to_q/to_k/to_v, SDPA, '
+                        'to_out + fused heat-map kernel), pinned-host inputs H2D every step, + compute_global_heat_map '
+                        '(+ all_gather when N>1) + D2H of the maps'},
+        'gpu_launches': launches,
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                     'traffic': recorded_traffic(args.workload), 'kernel': 'daam accumulate (softmax(QK^T)->unravel->+=)',
+                     'algorithmic_bytes_per_launch': bytes_step, 'peak_source': peak_src},
+        'cpu_baseline': cpu,
+        'hook_overhead': overhead,
+    }
+    print(json.dumps(line), flush=True)
+    D.close()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,131 @@
+"""ctypes binding of ``libdaam_b200.so`` (C ABI: ``include/daam_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` (``daam_b200/build.py``). There is no CPU or torch
+fallback behind these calls: if the shared object is missing, or a call fails, the caller gets an exception.
+ctypes releases the GIL around every foreign call.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence
+
+LIB_NAME = 'libdaam_b200.so'
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+
+DAAM_F32, DAAM_F16, DAAM_BF16 = 0, 1, 2
+ACC_AUTO, ACC_FORCE_SIMT, ACC_FORCE_MMA = 0, 1, 2
+ACC_RMW_AUTO, ACC_RMW_LDST, ACC_RMW_RED = 0x00, 0x10, 0x20
+E_INVALID, E_UNSUPPORTED, E_CUDA = -1, -2, -3
+TOKENS = 77
+
+EXPORTS = ('daam_accumulate', 'daam_finalize', 'daam_word_heat_map', 'daam_expand_as', 'daam_abi_version',
+           'daam_last_error', 'daam_device_info', 'daam_launch_count')
+
+
+class DaamLayer(ctypes.Structure):
+    """``struct daam_layer`` (include/daam_b200.h)."""
+    _fields_ = [
+        ('q', ctypes.c_void_p), ('k', ctypes.c_void_p), ('acc', ctypes.c_void_p),
+        ('q_stride_prompt', ctypes.c_int64), ('q_stride_pixel', ctypes.c_int64), ('q_stride_head', ctypes.c_int64),
+        ('k_stride_prompt', ctypes.c_int64), ('k_stride_token', ctypes.c_int64), ('k_stride_head', ctypes.c_int64),
+        ('n_prompts', ctypes.c_int32), ('heads', ctypes.c_int32), ('hw', ctypes.c_int32), ('tokens', ctypes.c_int32),
+        ('head_dim', ctypes.c_int32), ('dtype', ctypes.c_int32), ('scale', ctypes.c_float),
+        ('reserved', ctypes.c_int32),
+    ]
+
+
+class DaamKeyGroup(ctypes.Structure):
+    """``struct daam_key_group`` (include/daam_b200.h)."""
+    _fields_ = [
+        ('acc', ctypes.c_void_p), ('heads', ctypes.c_int32), ('h', ctypes.c_int32), ('w', ctypes.c_int32),
+        ('tokens', ctypes.c_int32), ('head_sel', ctypes.c_int32), ('reserved', ctypes.c_int32),
+    ]
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f'libdaam_b200: {message} (status {code})')
+        self.code = code
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the in-tree library once and declare the prototypes. Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError(
+            f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            f'(or `python -m daam_b200.build`). daam_b200 has no CPU fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    i32, u32, i64, vp, f32 = ctypes.c_int32, ctypes.c_uint32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float
+    lib.daam_accumulate.argtypes = [ctypes.POINTER(DaamLayer), i32, u32, vp]
+    lib.daam_accumulate.restype = ctypes.c_int
+    lib.daam_finalize.argtypes = [ctypes.POINTER(DaamKeyGroup), i32, i32, i32, i32, vp, vp]
+    lib.daam_finalize.restype = ctypes.c_int
+    lib.daam_word_heat_map.argtypes = [vp, i32, i32, ctypes.POINTER(i32), i32, vp, vp]
+    lib.daam_word_heat_map.restype = ctypes.c_int
+    lib.daam_expand_as.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp]
+    lib.daam_expand_as.restype = ctypes.c_int
+    lib.daam_abi_version.argtypes = []
+    lib.daam_abi_version.restype = ctypes.c_int
+    lib.daam_last_error.argtypes = []
+    lib.daam_last_error.restype = ctypes.c_char_p
+    lib.daam_device_info.argtypes = [ctypes.POINTER(i32)] * 3
+    lib.daam_device_info.restype = ctypes.c_int
+    lib.daam_launch_count.argtypes = []
+    lib.daam_launch_count.restype = i64
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise NativeError(rc, load().daam_last_error().decode('utf-8', 'replace'))
+
+
+def accumulate(layers: Sequence[DaamLayer], stream: int, flags: int = ACC_AUTO):
+    n = len(layers)
+    if n == 0:
+        return
+    arr = (DaamLayer * n)(*layers)
+    _check(load().daam_accumulate(arr, n, flags, ctypes.c_void_p(stream)))
+
+
+def finalize(groups: Sequence[DaamKeyGroup], x: int, n_rows: int, normalize: bool, out_ptr: int, stream: int):
+    n = len(groups)
+    arr = (DaamKeyGroup * max(n, 1))(*groups)
+    _check(load().daam_finalize(arr, n, x, n_rows, int(bool(normalize)), ctypes.c_void_p(out_ptr),
+                                ctypes.c_void_p(stream)))
+
+
+def word_heat_map(maps_ptr: int, n_rows: int, x: int, rows: Sequence[int], out_ptr: int, stream: int):
+    arr = (ctypes.c_int32 * max(len(rows), 1))(*rows)
+    _check(load().daam_word_heat_map(ctypes.c_void_p(maps_ptr), n_rows, x, arr, len(rows), ctypes.c_void_p(out_ptr),
+                                     ctypes.c_void_p(stream)))
+
+
+def expand_as(map_ptr: int, x: int, out_h: int, out_w: int, absolute: bool, threshold: Optional[float], out_ptr: int,
+              scratch_ptr: int, stream: int):
+    use_thr = bool(threshold)   # the reference's `if threshold:` (daam/heatmap.py:87)
+    _check(load().daam_expand_as(ctypes.c_void_p(map_ptr), x, out_h, out_w, int(bool(absolute)), int(use_thr),
+                                 float(threshold) if use_thr else 0.0, ctypes.c_void_p(out_ptr),
+                                 ctypes.c_void_p(scratch_ptr), ctypes.c_void_p(stream)))
+
+
+def device_info():
+    sm, major, minor = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    _check(load().daam_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)))
+    return {'sm_count': sm.value, 'cc': (major.value, minor.value)}
+
+
+def launch_count() -> int:
+    return int(load().daam_launch_count())
+
+
+def abi_version() -> int:
+    return int(load().daam_abi_version())

@@ -1,0 +1,241 @@
+// Finalize kernels: per-key bicubic upsample -> clamp -> mean over keys (-> normalise), word-map row mean,
+// and the image-size expansion of a word map.
+//
+// Replaces DiffusionHeatMapHooker.compute_global_heat_map (daam/trace.py:109-130), GlobalHeatMap.
+// compute_word_heat_map (daam/heatmap.py:121-123) and WordHeatMap.expand_as (daam/heatmap.py:77-93).
+// The interpolation is torch's `upsample_bicubic2d` with align_corners=False: source index
+// (dst + 0.5) * in/out - 0.5 (not clamped), Keys' cubic convolution with A = -0.75 on the 4 taps floor-1..floor+2,
+// taps clamped to the border; rows are combined horizontally first, then vertically, all in fp32.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace daam {
+namespace {
+
+constexpr int kMaxGroups = 160;   // key groups (layer x prompt slices) per finalize launch
+constexpr int kMaxRows = 128;     // selected rows of a word map
+
+struct FinalizeParams {
+  int n_groups, x, n_rows, n_keys;
+  daam_key_group g[kMaxGroups];
+};
+
+struct Taps {
+  int idx[4];
+  float w[4];
+};
+
+__device__ __forceinline__ float cubic_near(float t, float a) { return ((a + 2.f) * t - (a + 3.f)) * t * t + 1.f; }
+__device__ __forceinline__ float cubic_far(float t, float a) { return ((a * t - 5.f * a) * t + 8.f * a) * t - 4.f * a; }
+
+__device__ __forceinline__ Taps make_taps(int dst, int n_in, int n_out) {
+  const float a = -0.75f;
+  const float scale = (float)n_in / (float)n_out;
+  const float src = scale * ((float)dst + 0.5f) - 0.5f;
+  const float fl = floorf(src);
+  const float t = src - fl;
+  const int base = (int)fl;
+  Taps r;
+  r.w[0] = cubic_far(t + 1.f, a);
+  r.w[1] = cubic_near(t, a);
+  r.w[2] = cubic_near(1.f - t, a);
+  r.w[3] = cubic_far(2.f - t, a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r.idx[i] = min(max(base - 1 + i, 0), n_in - 1);
+  return r;
+}
+
+__device__ __forceinline__ float bicubic_at(const float* __restrict__ src, int w, const Taps& ty, const Taps& tx) {
+  float v = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float* row = src + ty.idx[i] * w;
+    float r = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r += tx.w[j] * __ldg(row + tx.idx[j]);
+    v += ty.w[i] * r;
+  }
+  return v;
+}
+
+// grid: (ceil(x*x / 256), n_rows). One thread = one output element (row t, pixel o); it walks every selected key.
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams P, float* __restrict__ out) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  const int x = P.x;
+  if (o >= x * x) return;
+  const int oy = o / x, ox = o - oy * x;
+  float sum = 0.f;
+  int ch = -1, cw = -1;
+  Taps ty, tx;
+  for (int g = 0; g < P.n_groups; ++g) {
+    const daam_key_group& G = P.g[g];
+    const int hw = G.h * G.w;
+    const int h0 = G.head_sel < 0 ? 0 : G.head_sel;
+    const int h1 = G.head_sel < 0 ? G.heads : G.head_sel + 1;
+    const bool same = (G.h == x && G.w == x);
+    if (!same && (G.h != ch || G.w != cw)) {
+      ty = make_taps(oy, G.h, x);
+      tx = make_taps(ox, G.w, x);
+      ch = G.h; cw = G.w;
+    }
+    const float* base = G.acc + (long long)t * hw;
+    const long long head_stride = (long long)G.tokens * hw;
+    if (same) {   // scale 1: the cubic weights are exactly (0, 1, 0, 0)
+#pragma unroll 4
+      for (int head = h0; head < h1; ++head) sum += fmaxf(__ldg(base + head * head_stride + o), 0.f);
+    } else {
+#pragma unroll 2
+      for (int head = h0; head < h1; ++head) sum += fmaxf(bicubic_at(base + head * head_stride, G.w, ty, tx), 0.f);
+    }
+  }
+  out[(long long)t * x * x + o] = sum / (float)P.n_keys;
+}
+
+// maps / (maps[1:-1].sum(0) + 1e-6), in place (daam/trace.py:129-130)
+__global__ void normalize_kernel(float* __restrict__ maps, int n_rows, int xx) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= xx) return;
+  float s = 0.f;
+  for (int t = 1; t < n_rows - 1; ++t) s += maps[(long long)t * xx + o];
+  s += 1e-6f;
+  for (int t = 0; t < n_rows; ++t) maps[(long long)t * xx + o] = maps[(long long)t * xx + o] / s;
+}
+
+struct RowSel {
+  int n;
+  int rows[kMaxRows];
+};
+
+__global__ void word_map_kernel(const float* __restrict__ maps, const __grid_constant__ RowSel sel, int xx,
+                                float* __restrict__ out) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= xx) return;
+  float s = 0.f;
+  for (int i = 0; i < sel.n; ++i) s += __ldg(maps + (long long)sel.rows[i] * xx + o);
+  out[o] = s / (float)sel.n;
+}
+
+// ---- expand_as ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ordered(float f) {   // monotone float -> uint map for atomicMin/Max
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unordered(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void expand_init_kernel(unsigned* mm) { mm[0] = 0xffffffffu; mm[1] = 0u; }
+
+__global__ void __launch_bounds__(256) expand_upsample_kernel(const float* __restrict__ src, int x, int oh, int ow,
+                                                              float* __restrict__ out, unsigned* mm) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  float v = 0.f;
+  const bool live = o < oh * ow;
+  if (live) {
+    const int oy = o / ow, ox = o - oy * ow;
+    const Taps ty = make_taps(oy, x, oh), tx = make_taps(ox, x, ow);
+    v = bicubic_at(src, x, ty, tx);
+    out[o] = v;
+  }
+  float lo = live ? v : INFINITY, hi = live ? v : -INFINITY;
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(mm, ordered(lo));
+    atomicMax(mm + 1, ordered(hi));
+  }
+}
+
+__global__ void expand_normalize_kernel(float* __restrict__ out, int n, const unsigned* __restrict__ mm, int absolute,
+                                        int use_threshold, float threshold) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n) return;
+  float v = out[o];
+  if (!absolute) {
+    const float lo = unordered(mm[0]), hi = unordered(mm[1]);
+    v = (v - lo) / (hi - lo + 1e-8f);
+  }
+  if (use_threshold) v = v > threshold ? 1.f : 0.f;
+  out[o] = v;
+}
+
+}  // namespace
+}  // namespace daam
+
+using namespace daam;
+
+extern "C" int daam_finalize(const daam_key_group* groups, int32_t n_groups, int32_t x, int32_t n_rows,
+                             int32_t normalize, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!groups || !out || x <= 0 || n_rows <= 0) { set_error("daam_finalize: null pointer or non-positive size"); return DAAM_E_INVALID; }
+  if (n_groups <= 0) { set_error("daam_finalize: no key selected"); return DAAM_E_INVALID; }
+  if (n_groups > kMaxGroups) { set_error("daam_finalize: %d key groups > %d", n_groups, kMaxGroups); return DAAM_E_UNSUPPORTED; }
+  DeviceInfo dev;
+  if (int rc = get_device_info(&dev)) return rc;
+  FinalizeParams p;
+  p.n_groups = n_groups; p.x = x; p.n_rows = n_rows; p.n_keys = 0;
+  for (int i = 0; i < n_groups; ++i) {
+    const daam_key_group& g = groups[i];
+    if (!g.acc || g.heads <= 0 || g.h <= 0 || g.w <= 0 || g.tokens < n_rows || g.head_sel >= g.heads) {
+      set_error("daam_finalize: bad key group %d (heads %d, h %d, w %d, tokens %d, head_sel %d, n_rows %d)", i, g.heads,
+                g.h, g.w, g.tokens, g.head_sel, n_rows);
+      return DAAM_E_INVALID;
+    }
+    p.g[i] = g;
+    p.n_keys += g.head_sel < 0 ? g.heads : 1;
+  }
+  const int xx = x * x;
+  dim3 grid((xx + 255) / 256, n_rows);
+  finalize_kernel<<<grid, 256, 0, stream>>>(p, out);
+  DAAM_CUDA_TRY(cudaGetLastError());
+  count_launch();
+  if (normalize) {
+    normalize_kernel<<<(xx + 255) / 256, 256, 0, stream>>>(out, n_rows, xx);
+    DAAM_CUDA_TRY(cudaGetLastError());
+    count_launch();
+  }
+  return DAAM_OK;
+}
+
+extern "C" int daam_word_heat_map(const float* global_maps, int32_t n_rows, int32_t x, const int32_t* rows,
+                                  int32_t n_sel, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!global_maps || !rows || !out || x <= 0 || n_sel <= 0) { set_error("daam_word_heat_map: null pointer or empty selection"); return DAAM_E_INVALID; }
+  if (n_sel > kMaxRows) { set_error("daam_word_heat_map: %d rows > %d", n_sel, kMaxRows); return DAAM_E_UNSUPPORTED; }
+  DeviceInfo dev;
+  if (int rc = get_device_info(&dev)) return rc;
+  RowSel sel;
+  sel.n = n_sel;
+  for (int i = 0; i < n_sel; ++i) {
+    int r = rows[i];
+    if (r < 0) r += n_rows;   // torch-style negative index
+    if (r < 0 || r >= n_rows) { set_error("daam_word_heat_map: row %d out of range [0, %d)", rows[i], n_rows); return DAAM_E_INVALID; }
+    sel.rows[i] = r;
+  }
+  const int xx = x * x;
+  word_map_kernel<<<(xx + 255) / 256, 256, 0, stream>>>(global_maps, sel, xx, out);
+  DAAM_CUDA_TRY(cudaGetLastError());
+  count_launch();
+  return DAAM_OK;
+}
+
+extern "C" int daam_expand_as(const float* word_map, int32_t x, int32_t out_h, int32_t out_w, int32_t absolute,
+                              int32_t use_threshold, float threshold, float* out, float* scratch, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!word_map || !out || !scratch || x <= 0 || out_h <= 0 || out_w <= 0) { set_error("daam_expand_as: null pointer or non-positive size"); return DAAM_E_INVALID; }
+  DeviceInfo dev;
+  if (int rc = get_device_info(&dev)) return rc;
+  unsigned* mm = reinterpret_cast<unsigned*>(scratch);
+  const int n = out_h * out_w;
+  expand_init_kernel<<<1, 1, 0, stream>>>(mm);
+  expand_upsample_kernel<<<(n + 255) / 256, 256, 0, stream>>>(word_map, x, out_h, out_w, out, mm);
+  expand_normalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out, n, mm, absolute, use_threshold, threshold);
+  DAAM_CUDA_TRY(cudaGetLastError());
+  count_launch(3);
+  return DAAM_OK;
+}

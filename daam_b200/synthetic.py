@@ -462,9 +462,15 @@ class SyntheticPipeline:
 
 
 def make_pipeline(spec: UNetSpec = SD21_SPEC, body: str = 'skeleton', dtype=torch.float32, device='cpu',
-                  seed: int = 0) -> SyntheticPipeline:
+                  seed: int = 0, init_on_device: bool = False) -> SyntheticPipeline:
+    """Random-init pipeline. Weights are drawn on the CPU from ``seed`` (identical on every box) unless
+    ``init_on_device`` (fast for the full-size bodies; values then depend on the device RNG)."""
     gen_state = torch.random.get_rng_state()
     torch.manual_seed(seed)
-    unet = SyntheticUNet(spec, body=body)
+    if init_on_device and torch.device(device).type == 'cuda':
+        with torch.device(device):
+            unet = SyntheticUNet(spec, body=body)
+    else:
+        unet = SyntheticUNet(spec, body=body)
     torch.random.set_rng_state(gen_state)
     return SyntheticPipeline(unet, dtype=dtype, device=device, seed=seed)

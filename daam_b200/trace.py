@@ -1,0 +1,311 @@
+"""The tracer: ``with trace(pipe) as tc: pipe(prompt); tc.compute_global_heat_map()`` on B200-native kernels.
+
+Mirror of the reference's L1 (``/root/reference/daam/trace.py``): same classes, constructor arguments, methods and
+exceptions; what differs is what runs underneath.
+
+* The attention processor (:class:`UNetCrossAttentionHooker`, reference trace.py:189-315) owns the whole attn2 forward
+  like the reference's, but never materialises the probabilities: the layer output comes from SDPA, and the
+  heat-map side of the call -- ``get_attention_scores`` + ``_unravel_attn`` + the per-head ``update`` loop (trace.py:
+  276, 219-244, 293-294) -- is one fused CUDA kernel (``daam_accumulate``) reading the Q/K projections in place.
+* Kernel work is queued per denoising step and issued as ONE persistent launch covering every traced layer of the step
+  (``launch='step'``, default) on a side stream, so it overlaps the next step's UNet forward; ``launch='layer'`` issues it
+  immediately per layer on the current stream.
+* ``compute_global_heat_map`` (trace.py:83-132) keeps the Python-side key filter and error messages and runs the
+  bicubic-upsample / clamp / mean / normalise reduction as one kernel (``daam_finalize``).
+
+Accumulators are fp32 regardless of the pipeline dtype (the reference accumulates in the pipeline dtype, SURVEY.md
+section 5); parity is stated against the fp32 oracle fed the same Q/K.
+"""
+from __future__ import annotations
+
+import math
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Type, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _native, ops
+from .heatmap import GlobalHeatMap, LayerSlab, RawHeatMapCollection
+from .hook import AggregateHooker, ObjectHooker, UNetCrossAttentionLocator
+from .utils import cache_dir
+
+__all__ = ['trace', 'DiffusionHeatMapHooker', 'GlobalHeatMap', 'UNetCrossAttentionHooker', 'PipelineHooker',
+           'ImageProcessorHooker']
+
+class DiffusionHeatMapHooker(AggregateHooker):
+    """Context manager that traces every located cross-attention layer of ``pipeline.unet`` (trace.py:22-59).
+
+    Extra keyword-only options (not in the reference): ``launch`` ('step' | 'layer', see module docstring),
+    ``batch_prompts`` (accept several prompts per generation: N independent single-prompt traces sharing each launch;
+    the reference rejects this, trace.py:172-173) and ``locate_middle_block`` (also locate the mid block without
+    enabling save/load of heads -- BASELINE config 5 "all 16+70 layers").
+    """
+
+    def __init__(self, pipeline, low_memory: bool = False, load_heads: bool = False, save_heads: bool = False,
+                 data_dir: str = None, *, launch: str = 'step', batch_prompts: bool = False,
+                 locate_middle_block: bool = False, kernel_flags: int = _native.ACC_AUTO):
+        if launch not in ('step', 'layer'):
+            raise ValueError("launch must be 'step' or 'layer'")
+        if load_heads or save_heads:
+            raise NotImplementedError(
+                'save_heads/load_heads need the materialised probabilities (reference trace.py:246-250, 279-282); '
+                'that compatibility path is listed as "next" in SURVEY.md section 8f and is not built yet')
+        _native.load()   # fail here, loudly, if the CUDA library is missing
+        self.all_heat_maps = RawHeatMapCollection()
+        side = pipeline.unet.config.sample_size * pipeline.vae_scale_factor
+        self.latent_hw = 4096 if side in (512, 1024) else 9216   # 64x64, or 96x96 for the 768-pixel models
+        self.locator = UNetCrossAttentionLocator(restrict={0} if low_memory else None,
+                                                 locate_middle_block=locate_middle_block or load_heads or save_heads)
+        self.last_prompt: str = ''
+        self.last_prompts: List[str] = []
+        self.last_image = None
+        self.time_idx = 0
+        self._gen_idx = 0
+        self.launch = launch
+        self.batch_prompts = batch_prompts
+        self.kernel_flags = kernel_flags
+        self._pending: List[tuple] = []        # (layer_idx, DaamLayer, q, k, acc) awaiting the step launch
+        self._pending_layers = set()
+        self._stream: Optional[torch.cuda.Stream] = None
+        self._dirty = False                    # side-stream work not yet ordered before the current stream
+        self.all_heat_maps.bind(self.synchronize, self._zero_slabs)
+
+        modules = [
+            UNetCrossAttentionHooker(m, self, layer_idx=idx, latent_hw=self.latent_hw, data_dir=data_dir)
+            for idx, m in enumerate(self.locator.locate(pipeline.unet))
+        ]
+        modules.append(PipelineHooker(pipeline, self))
+        if type(pipeline).__name__ == 'StableDiffusionXLPipeline' and getattr(pipeline, 'image_processor', None):
+            modules.append(ImageProcessorHooker(pipeline.image_processor, self))
+        super().__init__(modules)
+        self.pipe = pipeline
+
+    # -- small reference API ------------------------------------------------------------------------------------------
+    def time_callback(self, *args, **kwargs):
+        self.time_idx += 1
+
+    @property
+    def layer_names(self):
+        return self.locator.layer_names
+
+    def to_experiment(self, path, seed=None, id='.', subtype='.', **compute_kwargs):
+        raise NotImplementedError('GenerationExperiment persistence (reference daam/experiment.py) is outside the '
+                                  'hot-path scope; use compute_global_heat_map().heat_maps')
+
+    def _unhook_impl(self):
+        self.flush()
+        super()._unhook_impl()
+
+    # -- kernel queue -------------------------------------------------------------------------------------------------
+    def _side_stream(self, device) -> torch.cuda.Stream:
+        if self._stream is None or self._stream.device != torch.device(device):
+            self._stream = torch.cuda.Stream(device=device)
+        return self._stream
+
+    def _enqueue(self, layer_idx: int, factor: int, q: torch.Tensor, k: torch.Tensor, heads: int, scale: float):
+        """Register one traced layer call: ``q [B, hw, C]``, ``k [B, 77, C]`` straight from ``to_q`` / ``to_k``."""
+        if not q.is_cuda:
+            raise RuntimeError('daam_b200 traces pipelines that live on a CUDA device only (there is no CPU fallback)')
+        bsz, hw, _ = q.shape
+        side = int(math.sqrt(hw))
+        if side * side != hw:
+            raise RuntimeError(f'layer {layer_idx}: {hw} query positions are not a square map')
+        if q.stride(-1) != 1 or k.stride(-1) != 1:
+            q, k = q.contiguous(), k.contiguous()
+        # "second half of the batch*heads axis" (trace.py:240): the conditional samples of a CFG batch
+        _, n_prompts, head0, n_heads = ops.cond_half(bsz, heads)
+        if n_prompts > 1 and not self.batch_prompts:
+            raise ValueError('Only single prompt generation is supported for heat map computation.')
+        slab = self.all_heat_maps.slab_for(layer_idx, factor, n_prompts, n_heads, side, side, q.device, head0)
+        desc = ops.make_layer_desc(q, k, slab.acc, heads, scale)
+        if self.launch == 'layer':
+            ops.accumulate([desc], q.device, flags=self.kernel_flags)
+            return
+        if layer_idx in self._pending_layers:   # the layer comes round again: a new UNet forward has started
+            self.flush()
+        self._pending.append((layer_idx, desc, q, k, slab.acc))   # tensors kept alive until the launch
+        self._pending_layers.add(layer_idx)
+
+    def flush(self):
+        """Issue the queued layer calls as one persistent launch on the side stream."""
+        if not self._pending:
+            return
+        device = self._pending[0][2].device
+        side = self._side_stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))       # Q/K were produced on the current stream
+        ops.accumulate([p[1] for p in self._pending], device, stream=side, flags=self.kernel_flags)
+        for _, _, q, k, _ in self._pending:                            # keep the projections alive until the kernel ran
+            q.record_stream(side)
+            k.record_stream(side)
+        self._pending.clear()
+        self._pending_layers.clear()
+        self._dirty = True
+
+    def synchronize(self):
+        """Make every accumulate issued so far visible to work enqueued on the current stream afterwards."""
+        self.flush()
+        if self._dirty and self._stream is not None:
+            torch.cuda.current_stream(self._stream.device).wait_stream(self._stream)
+            self._dirty = False
+
+    def _zero_slabs(self, slabs: List[LayerSlab]):
+        if not slabs:
+            return
+        self.synchronize()
+        for slab in slabs:
+            slab.acc.zero_()
+        if self._stream is not None:   # later side-stream launches must see the zeroed slabs
+            self._stream.wait_stream(torch.cuda.current_stream(slabs[0].acc.device))
+
+    # -- finalize -------------------------------------------------------------------------------------------------------
+    def compute_global_heat_map(self, prompt=None, factors=None, head_idx=None, layer_idx=None, normalize=False,
+                                prompt_idx: int = 0) -> GlobalHeatMap:
+        """Aggregate across time (already summed in the slabs) and across layers/heads (trace.py:83-132).
+
+        Args mirror the reference: ``factors`` restricts the spatial factors, ``head_idx`` / ``layer_idx`` restrict to one
+        head / layer, ``normalize`` divides by the per-pixel sum over the real tokens. ``prompt_idx`` selects the prompt in
+        ``batch_prompts`` mode.
+        """
+        if prompt is None:
+            prompt = self.last_prompts[prompt_idx] if self.last_prompts else self.last_prompt
+        factors = {0, 1, 2, 4, 8, 16, 32, 64} if factors is None else set(factors)
+        x = int(np.sqrt(self.latent_hw))
+        self.synchronize()
+        groups, keep = [], []
+        for slab in self.all_heat_maps.live_slabs():
+            if slab.factor not in factors or (layer_idx is not None and layer_idx != slab.layer_idx):
+                continue
+            if head_idx is not None and not 0 <= head_idx < slab.heads:
+                continue
+            acc = slab.acc[prompt_idx]
+            groups.append(_native.DaamKeyGroup(acc=acc.data_ptr(), heads=slab.heads, h=slab.h, w=slab.w,
+                                               tokens=acc.shape[1], head_sel=-1 if head_idx is None else head_idx,
+                                               reserved=0))
+            keep.append(acc)
+        if not groups:
+            if head_idx is not None or layer_idx is not None:
+                raise RuntimeError('No heat maps found for the given parameters.')
+            raise RuntimeError('No heat maps found. Did you forget to call `with trace(...)` during generation?')
+        n_rows = min(len(self.pipe.tokenizer.tokenize(prompt)) + 2, _native.TOKENS)   # 1 for SOS and 1 for padding
+        device = keep[0].device
+        maps = torch.empty((n_rows, x, x), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            _native.finalize(groups, x, n_rows, normalize, maps.data_ptr(),
+                             torch.cuda.current_stream(device).cuda_stream)
+        return GlobalHeatMap(self.pipe.tokenizer, prompt, maps)
+
+
+class ImageProcessorHooker(ObjectHooker):
+    """Remembers the first post-processed image of an SDXL pipeline (trace.py:135-147)."""
+
+    def __init__(self, processor, parent_trace: 'trace'):
+        super().__init__(processor)
+        self.parent_trace = parent_trace
+
+    def _hooked_postprocess(hk_self, _, *args, **kwargs):
+        images = hk_self.monkey_super('postprocess', *args, **kwargs)
+        hk_self.parent_trace.last_image = images[0]
+        return images
+
+    def _hook_impl(self):
+        self.monkey_patch('postprocess', self._hooked_postprocess)
+
+
+class PipelineHooker(ObjectHooker):
+    """Per-generation reset + prompt capture at ``check_inputs``; image capture at the safety checker (trace.py:150-186)."""
+
+    def __init__(self, pipeline, parent_trace: 'trace'):
+        super().__init__(pipeline)
+        self.heat_maps = parent_trace.all_heat_maps
+        self.parent_trace = parent_trace
+
+    def _hooked_run_safety_checker(hk_self, self, image, *args, **kwargs):
+        image, has_nsfw = hk_self.monkey_super('run_safety_checker', image, *args, **kwargs)
+        processor = getattr(self, 'image_processor', None)
+        if processor:
+            images = processor.postprocess(image, output_type='pil') if torch.is_tensor(image) \
+                else processor.numpy_to_pil(image)
+        else:
+            images = self.numpy_to_pil(image)
+        hk_self.parent_trace.last_image = images[len(images) - 1]
+        return image, has_nsfw
+
+    def _hooked_check_inputs(hk_self, _, prompt: Union[str, List[str]], *args, **kwargs):
+        tr = hk_self.parent_trace
+        if isinstance(prompt, str):
+            prompts = [prompt]
+        else:
+            prompts = list(prompt)
+            if len(prompts) > 1 and not tr.batch_prompts:
+                raise ValueError('Only single prompt generation is supported for heat map computation.')
+        hk_self.heat_maps.clear()
+        tr.last_prompt = prompts[0]
+        tr.last_prompts = prompts
+        return hk_self.monkey_super('check_inputs', prompt, *args, **kwargs)
+
+    def _hook_impl(self):
+        self.monkey_patch('run_safety_checker', self._hooked_run_safety_checker, strict=False)  # absent in SDXL
+        self.monkey_patch('check_inputs', self._hooked_check_inputs)
+
+
+class UNetCrossAttentionHooker(ObjectHooker):
+    """The attention processor installed on one ``attn2`` module (trace.py:189-315)."""
+
+    def __init__(self, module, parent_trace: 'trace', context_size: int = 77, layer_idx: int = 0,
+                 latent_hw: int = 9216, load_heads: bool = False, save_heads: bool = False,
+                 data_dir: Union[str, Path] = None):
+        super().__init__(module)
+        self.heat_maps = parent_trace.all_heat_maps
+        self.context_size = context_size
+        self.layer_idx = layer_idx
+        self.latent_hw = latent_hw
+        self.load_heads = load_heads
+        self.save_heads = save_heads
+        self.trace = parent_trace
+        self.data_dir = Path(data_dir) if data_dir is not None else cache_dir() / 'heads'
+
+    @torch.no_grad()
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None):
+        """attn2 forward: projections -> (heat-map kernel on Q/K) -> SDPA -> output projection."""
+        if attention_mask is not None:
+            raise RuntimeError('the heat-map kernel does not take an attention mask (SD cross-attention passes none)')
+        bsz, n, _ = hidden_states.shape
+        query = attn.to_q(hidden_states)
+        if encoder_hidden_states is None:
+            encoder_hidden_states = hidden_states
+        elif attn.norm_cross is not None:
+            encoder_hidden_states = attn.norm_cross(encoder_hidden_states)
+        key = attn.to_k(encoder_hidden_states)
+        value = attn.to_v(encoder_hidden_states)
+
+        heads = attn.heads
+        tokens = key.shape[1]
+        factor = int(math.sqrt(self.latent_hw // n))
+        self.trace._gen_idx += 1
+        if tokens == self.context_size and factor != 8:      # skip if too large (trace.py:289)
+            self.trace._enqueue(self.layer_idx, factor, query, key, heads, attn.scale)
+
+        d = query.shape[-1] // heads
+        q4 = query.view(bsz, n, heads, d).transpose(1, 2)
+        k4 = key.view(bsz, tokens, heads, d).transpose(1, 2)
+        v4 = value.view(bsz, tokens, heads, d).transpose(1, 2)
+        out = F.scaled_dot_product_attention(q4, k4, v4, scale=attn.scale)
+        out = out.transpose(1, 2).reshape(bsz, n, heads * d)
+        out = attn.to_out[0](out)    # linear proj
+        return attn.to_out[1](out)   # dropout
+
+    def _hook_impl(self):
+        self.original_processor = self.module.processor
+        self.module.set_processor(self)
+
+    def _unhook_impl(self):
+        self.module.set_processor(self.original_processor)
+
+    @property
+    def num_heat_maps(self):
+        return len(self.heat_maps)
+
+
+trace: Type[DiffusionHeatMapHooker] = DiffusionHeatMapHooker

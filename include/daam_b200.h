@@ -1,0 +1,130 @@
+/*
+ * daam_b200.h -- C ABI of libdaam_b200.so: the B200 (sm_100a) cross-attention heat-map hot path.
+ *
+ * The reference (castorini/daam, paths below relative to /root/reference) is pure Python/torch and has no FFI. The
+ * entry points here are what a binding for its hot path replaces; each one cites the reference interface it stands
+ * in for. INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer named *device* is CUDA device memory owned by the caller (torch
+ *    tensors on the Python side); the library never allocates or frees caller-visible memory;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it; the caller keeps the
+ *    buffers alive until the stream has passed the call;
+ *  - every function returns 0 on success and a negative DAAM_E_* code otherwise; daam_last_error() gives the message
+ *    of the calling thread's last failure (the Python host raises RuntimeError / ValueError like the reference does,
+ *    daam/hook.py:36-37, daam/trace.py:120-124);
+ *  - there is no CPU fallback: without a CUDA device every compute entry point fails with DAAM_E_CUDA.
+ */
+#ifndef DAAM_B200_H
+#define DAAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAAM_ABI_VERSION 1
+#define DAAM_TOKENS 77          /* context length the reference traces (daam/trace.py:194, guard at :289) */
+#define DAAM_MAX_HEAD_DIM 160   /* SD-1.x deepest level: 1280 channels / 8 heads */
+
+enum daam_status {
+  DAAM_OK = 0,
+  DAAM_E_INVALID = -1,          /* bad argument (shape, alignment, null pointer) */
+  DAAM_E_UNSUPPORTED = -2,      /* tokens != 77, head_dim not a multiple of 8 or > DAAM_MAX_HEAD_DIM, ... */
+  DAAM_E_CUDA = -3              /* a CUDA runtime call failed (including: no device) */
+};
+
+enum daam_dtype { DAAM_F32 = 0, DAAM_F16 = 1, DAAM_BF16 = 2 };
+
+/* daam_accumulate flags */
+#define DAAM_ACC_AUTO        0u  /* tcgen05 path for 16-bit inputs with head_dim 64, SIMT fp32 path otherwise */
+#define DAAM_ACC_FORCE_SIMT  1u  /* always the SIMT fp32 ("warp dot") kernel */
+#define DAAM_ACC_FORCE_MMA   2u  /* tcgen05 kernel or DAAM_E_UNSUPPORTED */
+#define DAAM_ACC_RMW_MASK   0x30u
+#define DAAM_ACC_RMW_AUTO   0x00u
+#define DAAM_ACC_RMW_LDST   0x10u /* coalesced load / add / store of the accumulator tile */
+#define DAAM_ACC_RMW_RED    0x20u /* red.global.add.f32 (SIMT) / bulk-async reduce-add from shared memory (MMA) */
+
+/*
+ * One traced cross-attention layer call: the conditional half of the projections `to_q(hidden_states)` and
+ * `to_k(encoder_hidden_states)` as the attention module emits them (daam/trace.py:262-270), *before* the reference's
+ * head_to_batch_dim permute (trace.py:272-273) -- the strides below express that permute, nothing is copied.
+ *
+ * Replaces, fused in one kernel: Attention.get_attention_scores = softmax(scale * Q K^T) (called at trace.py:276),
+ * UNetCrossAttentionHooker._unravel_attn (trace.py:219-244: token-major transpose, (h, w) reshape, "second half of the
+ * batch*heads axis" = conditional samples) and the per-head RawHeatMapCollection.update loop (trace.py:293-294,
+ * heatmap.py:153-156).
+ *
+ *   acc[p][head][t][pixel] += softmax_t( scale * <q[p][pixel][head][:], k[p][t][head][:]> )
+ *
+ * `acc` is fp32, contiguous [n_prompts][heads][tokens][hw]: acc[p][head] is exactly the reference's per-key
+ * [77, h, w] heat map for key (factor, layer, head). n_prompts > 1 is the batched mode (independent single-prompt
+ * traces run in one launch); the reference itself is single-prompt (trace.py:172-173).
+ */
+typedef struct daam_layer {
+  const void* q;             /* device; element (prompt 0, pixel 0, head 0, dim 0) of the CONDITIONAL half */
+  const void* k;             /* device; element (prompt 0, token 0, head 0, dim 0) of the conditional half */
+  float* acc;                /* device; fp32 [n_prompts][heads][tokens][hw], 16-byte aligned */
+  int64_t q_stride_prompt, q_stride_pixel, q_stride_head;   /* in elements; the head_dim axis is contiguous */
+  int64_t k_stride_prompt, k_stride_token, k_stride_head;
+  int32_t n_prompts, heads, hw, tokens, head_dim;
+  int32_t dtype;             /* enum daam_dtype of q and k */
+  float scale;               /* attn.scale = head_dim ** -0.5 */
+  int32_t reserved;
+} daam_layer;
+
+/* Enqueue the fused softmax(QK^T) -> unravel -> accumulate kernel over `n_layers` layer calls (any number; the
+ * library packs them into as few persistent launches as possible). `layers` is host memory, read before returning. */
+int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint32_t flags, void* stream);
+
+/*
+ * All (or one) heads of one traced layer: `acc` points at [heads][tokens][h*w] fp32 (one prompt's slice of the
+ * accumulator daam_accumulate fills). head_sel = -1 selects every head, otherwise one head index.
+ */
+typedef struct daam_key_group {
+  const float* acc;          /* device */
+  int32_t heads, h, w, tokens;
+  int32_t head_sel;
+  int32_t reserved;
+} daam_key_group;
+
+/*
+ * Replaces DiffusionHeatMapHooker.compute_global_heat_map (daam/trace.py:83-132) after its Python-side key filter:
+ * per selected key bicubic upsample (align_corners=False, A=-0.75, no antialias) to (x, x), clamp(min=0), mean over
+ * the keys, keep rows [0, n_rows), and if `normalize` divide by (sum of rows 1..n_rows-2 + 1e-6) per pixel.
+ * out: device fp32 [n_rows][x][x]. `groups` is host memory. Fails with DAAM_E_INVALID when no key is selected (the
+ * host turns that into the reference's "No heat maps found" RuntimeError, trace.py:120-124).
+ */
+int daam_finalize(const daam_key_group* groups, int32_t n_groups, int32_t x, int32_t n_rows, int32_t normalize,
+                  float* out, void* stream);
+
+/*
+ * Replaces GlobalHeatMap.compute_word_heat_map's tensor part (daam/heatmap.py:121-123): mean over the rows
+ * `rows[0..n_sel)` (host array, already offset by +1 for SOS as daam/utils.py:91 does) of global_maps [n_rows][x][x]
+ * -> out [x][x] (both device fp32).
+ */
+int daam_word_heat_map(const float* global_maps, int32_t n_rows, int32_t x, const int32_t* rows, int32_t n_sel,
+                       float* out, void* stream);
+
+/*
+ * Replaces WordHeatMap.expand_as's tensor part (daam/heatmap.py:77-93): bicubic upsample of word_map [x][x] to
+ * [out_h][out_w], then unless `absolute` (im - min) / (max - min + 1e-8), then if `use_threshold` binarise
+ * (im > threshold) (the reference's `if threshold:` -- Python truthiness -- is resolved by the host).
+ * out: device fp32 [out_h][out_w]; scratch: device, >= 2 floats (min/max), owned by the caller.
+ */
+int daam_expand_as(const float* word_map, int32_t x, int32_t out_h, int32_t out_w, int32_t absolute,
+                   int32_t use_threshold, float threshold, float* out, float* scratch, void* stream);
+
+/* Library / device introspection. */
+int daam_abi_version(void);
+const char* daam_last_error(void);
+/* sm_count, compute capability and the number of kernels this library has launched since load (bench.py's
+ * gpu_launches). Any out pointer may be NULL. Returns DAAM_E_CUDA without a device. */
+int daam_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+int64_t daam_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAAM_B200_H */

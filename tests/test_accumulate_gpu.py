@@ -1,0 +1,224 @@
+"""Parity of the fused softmax(QK^T) -> unravel -> accumulate kernel (through the C ABI) with the oracle and with the
+golden vectors the verbatim reference produced. Tolerances (stated per SURVEY.md section 8c):
+
+* fp32 inputs, SIMT path: rtol 1e-5 of the map's max, i.e. |err| <= 1e-5 * max|ref| (+1e-7) per element;
+* fp16/bf16 inputs: the oracle is fed the same (half-rounded) values in fp32; same bound x 20 (tensor-core
+  accumulation order and ex2.approx differ from torch's fp32 softmax).
+"""
+import numpy as np
+import pytest
+import torch
+
+from daam_b200 import _native, ops
+from tests.util import LAYER_FIXTURES, golden, oracle_layer_maps, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+TOL = {torch.float32: 1e-5, torch.float16: 2e-4, torch.bfloat16: 2e-4}
+
+PATHS = [
+    ('simt-ldst', _native.ACC_FORCE_SIMT | _native.ACC_RMW_LDST),
+    ('simt-red', _native.ACC_FORCE_SIMT | _native.ACC_RMW_RED),
+    ('auto', _native.ACC_AUTO),
+]
+
+
+def assert_close(got, ref, tol, what=''):
+    ref = torch.as_tensor(ref)
+    err = rel_err(got, ref)
+    assert err <= tol, f'{what}: max|err|/max|ref| = {err:.3e} > {tol:.1e}'
+
+
+@pytest.mark.parametrize('path,flags', PATHS)
+@pytest.mark.parametrize('name', LAYER_FIXTURES)
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+def test_golden_layers(name, dtype, path, flags):
+    """Reference outputs (fixtures) vs the kernel. The fixture inputs are fp16-representable, so the fp16 run reads
+    exactly the values the reference saw."""
+    fx = golden(name)
+    q = torch.from_numpy(fx['q']).to(DEV, dtype)
+    k = torch.from_numpy(fx['k']).to(DEV, dtype)
+    heads = int(fx['heads'])
+    acc = ops.accumulate_layer(q, k, heads, float(fx['scale']), flags=flags)
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(fx['maps']).reshape(1, heads, 77, -1)
+    assert_close(acc, ref, TOL[dtype], f'{name}/{path}')
+
+
+SHAPES = [  # hw, heads, head_dim  (SD-2.1 / SDXL layer shapes, SD-1.x head dims, 96-latent partial tiles)
+    (4096, 5, 64), (1024, 10, 64), (256, 20, 64), (4096, 10, 64), (1024, 20, 64),
+    (1024, 8, 80), (256, 8, 160), (4096, 8, 40), (576, 10, 64), (2304, 5, 64), (144, 20, 64), (16, 2, 64),
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize('hw,heads,d', SHAPES)
+def test_seeded_shapes_vs_oracle(hw, heads, d, dtype):
+    g = torch.Generator().manual_seed(hw * 131 + heads * 7 + d)
+    q = (torch.randn(2, hw, heads * d, generator=g) * 1.5).to(dtype).to(DEV)
+    k = torch.randn(2, 77, heads * d, generator=g).to(dtype).to(DEV)
+    acc = ops.accumulate_layer(q, k, heads)
+    torch.cuda.synchronize()
+    ref = oracle_layer_maps(q, k, heads, d ** -0.5).unsqueeze(0)
+    assert_close(acc, ref, TOL[dtype], f'hw{hw} H{heads} d{d} {dtype}')
+    # softmax rows sum to one -> every head sums to hw
+    sums = acc.double().sum(dim=(2, 3))
+    assert torch.allclose(sums, torch.full_like(sums, float(hw)), rtol=1e-5)
+    assert (acc >= 0).all()
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('path,flags', PATHS)
+def test_time_accumulation_and_linearity(dtype, path, flags):
+    """acc is a running sum over steps (daam/heatmap.py:153-156): 3 different steps, then the same step twice more."""
+    hw, heads, d = 1024, 4, 64
+    g = torch.Generator().manual_seed(5)
+    acc = ops.new_accumulator(1, heads, hw, DEV)
+    ref = torch.zeros(heads, 77, hw)
+    for step in range(3):
+        q = torch.randn(2, hw, heads * d, generator=g).to(dtype).to(DEV)
+        k = torch.randn(2, 77, heads * d, generator=g).to(dtype).to(DEV)
+        ops.accumulate_layer(q, k, heads, acc=acc, flags=flags)
+        ref += oracle_layer_maps(q, k, heads, d ** -0.5)
+    torch.cuda.synchronize()
+    assert_close(acc[0], ref, TOL[dtype], path)
+    before = acc.clone()
+    one = ops.accumulate_layer(q, k, heads, flags=flags)
+    ops.accumulate_layer(q, k, heads, acc=acc, flags=flags)
+    ops.accumulate_layer(q, k, heads, acc=acc, flags=flags)
+    torch.cuda.synchronize()
+    assert_close(acc - before, 2 * one, 1e-6, 'linearity')
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+def test_batched_prompts_equal_independent_traces(dtype):
+    """[uncond x N, cond x N] in one launch == N single-prompt calls (batched = N independent traces)."""
+    n, hw, heads, d = 3, 256, 4, 64
+    g = torch.Generator().manual_seed(9)
+    q = torch.randn(2 * n, hw, heads * d, generator=g).to(dtype).to(DEV)
+    k = torch.randn(2 * n, 77, heads * d, generator=g).to(dtype).to(DEV)
+    acc = ops.accumulate_layer(q, k, heads)
+    assert acc.shape == (n, heads, 77, hw)
+    for p in range(n):
+        pair_q = torch.stack([q[p], q[n + p]])
+        pair_k = torch.stack([k[p], k[n + p]])
+        single = ops.accumulate_layer(pair_q, pair_k, heads)
+        torch.cuda.synchronize()
+        assert torch.equal(single[0], acc[p])
+        assert_close(acc[p], oracle_layer_maps(pair_q, pair_k, heads, d ** -0.5), TOL[dtype], f'prompt {p}')
+
+
+def test_single_sample_keeps_upper_half_of_heads():
+    """Without a CFG pair the reference's `map_[map_.size(0)//2:]` keeps heads H/2.. (daam/trace.py:240)."""
+    hw, heads, d = 256, 6, 64
+    g = torch.Generator().manual_seed(2)
+    q = torch.randn(1, hw, heads * d, generator=g).to(DEV)
+    k = torch.randn(1, 77, heads * d, generator=g).to(DEV)
+    acc = ops.accumulate_layer(q, k, heads)
+    torch.cuda.synchronize()
+    assert acc.shape == (1, heads // 2, 77, hw)
+    ref = oracle_layer_maps(q, k, heads, d ** -0.5)     # the oracle applies the same rule: 3 maps
+    assert ref.shape[0] == heads // 2
+    assert_close(acc[0], ref, 1e-5)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+def test_strided_and_unaligned_views(dtype):
+    """q/k as slices of wider buffers (row stride != heads*d) and at element offsets that break 16-byte alignment."""
+    hw, heads, d = 256, 2, 64
+    g = torch.Generator().manual_seed(4)
+    wide_q = torch.randn(2, hw, heads * d + 24, generator=g).to(dtype).to(DEV)
+    wide_k = torch.randn(2, 77, heads * d + 24, generator=g).to(dtype).to(DEV)
+    for off in (0, 8, 3):    # 8 elements keeps fp16 rows 16-byte aligned, 3 does not
+        q, k = wide_q[:, :, off:off + heads * d], wide_k[:, :, off:off + heads * d]
+        acc = ops.accumulate_layer(q, k, heads)
+        torch.cuda.synchronize()
+        assert_close(acc[0], oracle_layer_maps(q.contiguous(), k.contiguous(), heads, d ** -0.5), TOL[dtype], f'off {off}')
+
+
+def test_many_layers_in_one_call_are_chunked():
+    """More layer calls than one parameter block holds (32): the library splits them into several launches."""
+    hw, heads, d, n_layers = 64, 2, 64, 45
+    g = torch.Generator().manual_seed(8)
+    qs = [torch.randn(2, hw, heads * d, generator=g).half().to(DEV) for _ in range(n_layers)]
+    ks = [torch.randn(2, 77, heads * d, generator=g).half().to(DEV) for _ in range(n_layers)]
+    accs = [ops.new_accumulator(1, heads, hw, DEV) for _ in range(n_layers)]
+    before = _native.launch_count()
+    ops.accumulate([ops.make_layer_desc(q, k, a, heads, d ** -0.5) for q, k, a in zip(qs, ks, accs)], DEV)
+    torch.cuda.synchronize()
+    assert _native.launch_count() - before == 2
+    for i in (0, 31, 32, 44):
+        assert_close(accs[i][0], oracle_layer_maps(qs[i], ks[i], heads, d ** -0.5), TOL[torch.float16], f'layer {i}')
+
+
+def test_mixed_dtypes_and_shapes_in_one_call():
+    g = torch.Generator().manual_seed(12)
+    cases = [(4096, 5, 64, torch.bfloat16), (256, 20, 64, torch.float16), (1024, 10, 64, torch.float32),
+             (1024, 8, 40, torch.float16)]
+    qs, ks, accs, descs = [], [], [], []
+    for hw, heads, d, dt in cases:
+        q = torch.randn(2, hw, heads * d, generator=g).to(dt).to(DEV)
+        k = torch.randn(2, 77, heads * d, generator=g).to(dt).to(DEV)
+        a = ops.new_accumulator(1, heads, hw, DEV)
+        qs.append(q), ks.append(k), accs.append(a)
+        descs.append(ops.make_layer_desc(q, k, a, heads, d ** -0.5))
+    ops.accumulate(descs, DEV)
+    torch.cuda.synchronize()
+    for (hw, heads, d, dt), q, k, a in zip(cases, qs, ks, accs):
+        assert_close(a[0], oracle_layer_maps(q, k, heads, d ** -0.5), TOL[dt], f'{hw}/{heads}/{d}/{dt}')
+
+
+def test_extreme_logits_stay_finite():
+    """Peaky rows (|logit| ~ 80) must neither overflow nor produce NaN; one-hot rows come out as exactly 0/1 sums."""
+    hw, heads, d = 256, 2, 64
+    g = torch.Generator().manual_seed(3)
+    q = (torch.randn(2, hw, heads * d, generator=g) * 10).half().to(DEV)
+    k = (torch.randn(2, 77, heads * d, generator=g) * 8).half().to(DEV)
+    acc = ops.accumulate_layer(q, k, heads)
+    torch.cuda.synchronize()
+    assert torch.isfinite(acc).all()
+    assert_close(acc[0], oracle_layer_maps(q, k, heads, d ** -0.5), 1e-3, 'peaky')
+
+
+def test_invalid_arguments_are_rejected():
+    q = torch.randn(2, 64, 128, device=DEV)
+    k76 = torch.randn(2, 76, 128, device=DEV)
+    acc = ops.new_accumulator(1, 2, 64, DEV)
+    with pytest.raises(_native.NativeError) as e:
+        ops.accumulate([ops.make_layer_desc(q, k76, acc, 2, 0.125)], DEV)
+    assert e.value.code == _native.E_UNSUPPORTED and '77' in str(e.value)
+    q12 = torch.randn(2, 64, 24, device=DEV)     # head_dim 12: not a multiple of 8
+    k12 = torch.randn(2, 77, 24, device=DEV)
+    with pytest.raises(_native.NativeError):
+        ops.accumulate([ops.make_layer_desc(q12, k12, acc, 2, 0.3)], DEV)
+    with pytest.raises(RuntimeError, match='accumulator must be'):
+        ops.make_layer_desc(q, torch.randn(2, 77, 128, device=DEV), ops.new_accumulator(1, 3, 64, DEV), 2, 0.125)
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        ops.make_layer_desc(q.cpu(), k76.cpu(), acc, 2, 0.125)
+
+
+def test_full_size_sd21_step_properties():
+    """BASELINE configs[1] sizes (all 15 SD-2.1 layers, bf16), checked through size-independent properties:
+    per-head sums == steps * hw, non-negativity, and step-linearity."""
+    shapes = [(256, 20)] * 3 + [(1024, 10)] * 3 + [(4096, 5)] * 3 + [(4096, 5)] * 2 + [(1024, 10)] * 2 + [(256, 20)] * 2
+    g = torch.Generator().manual_seed(21)
+    qs = [torch.randn(2, hw, h * 64, generator=g).bfloat16().to(DEV) for hw, h in shapes]
+    ks = [torch.randn(2, 77, h * 64, generator=g).bfloat16().to(DEV) for hw, h in shapes]
+    accs = [ops.new_accumulator(1, h, hw, DEV) for hw, h in shapes]
+    descs = [ops.make_layer_desc(q, k, a, h, 0.125) for q, k, a, (hw, h) in zip(qs, ks, accs, shapes)]
+    steps = 4
+    for _ in range(steps):
+        ops.accumulate(descs, DEV)
+    torch.cuda.synchronize()
+    for a, (hw, h) in zip(accs, shapes):
+        sums = a.double().sum(dim=(2, 3))
+        assert torch.allclose(sums, torch.full_like(sums, float(steps * hw)), rtol=2e-5)
+        assert (a >= 0).all()
+    one = [ops.accumulate_layer(q, k, h) for q, k, (hw, h) in zip(qs, ks, shapes)]
+    torch.cuda.synchronize()
+    for a, o in zip(accs, one):
+        assert_close(a, steps * o, 1e-6, 'steps x single')
+    # and one layer of each resolution against the oracle at full size
+    for i in (0, 3, 6):
+        hw, h = shapes[i]
+        assert_close(one[i][0], oracle_layer_maps(qs[i], ks[i], h, 0.125), TOL[torch.bfloat16], f'layer {i}')

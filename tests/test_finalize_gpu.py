@@ -1,0 +1,119 @@
+"""Parity of the finalize / word-map / expand kernels with the reference's outputs (golden fixtures) and the oracle.
+
+Tolerance: rtol 1e-5 of the output's max (+1e-6 abs): only fp32 summation order differs (SURVEY.md section 8c proposes
+rtol 1e-4 for the global map; the kernels are well inside it)."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from daam_b200 import _native
+from daam_b200.heatmap import GlobalHeatMap, WordHeatMap
+from daam_b200.synthetic import WhitespaceTokenizer
+from oracle import daam_oracle as O
+from tests.util import golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def fixture_groups(fx, select=lambda f, l, h: True, head_sel=None):
+    """Key tensors of the fixture grouped per layer (heads stacked): what the tracer's slabs look like."""
+    by_layer = {}
+    for name in fx.files:
+        if name.startswith('key_'):
+            f, l, h = (int(v) for v in name.split('_')[1:])
+            by_layer.setdefault(l, {})[h] = (f, torch.from_numpy(fx[name]))
+    groups, keep = [], []
+    for l in sorted(by_layer):
+        heads = by_layer[l]
+        f = heads[0][0]
+        if not select(f, l, None):
+            continue
+        if head_sel is not None and head_sel not in heads:
+            continue
+        t = torch.stack([heads[h][1] for h in sorted(heads)]).to(DEV)       # [H, tokens, h, w]
+        keep.append(t)
+        groups.append(_native.DaamKeyGroup(acc=t.data_ptr(), heads=t.shape[0], h=t.shape[2], w=t.shape[3],
+                                           tokens=t.shape[1], head_sel=-1 if head_sel is None else head_sel,
+                                           reserved=0))
+    return groups, keep
+
+
+def run_finalize(groups, n_rows, normalize=False, x=64):
+    out = torch.empty(n_rows, x, x, device=DEV)
+    _native.finalize(groups, x, n_rows, normalize, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize('case,select,head_sel,normalize', [
+    ('global', lambda f, l, h: True, None, False),
+    ('global_norm', lambda f, l, h: True, None, True),
+    ('factors_2_4', lambda f, l, h: f in (2, 4), None, False),
+    ('layer_1', lambda f, l, h: l == 1, None, False),
+    ('head_1', lambda f, l, h: True, 1, False),
+    ('layer_2_head_0', lambda f, l, h: l == 2, 0, False),
+])
+def test_finalize_golden(case, select, head_sel, normalize):
+    fx = golden('finalize')
+    groups, keep = fixture_groups(fx, select, head_sel)
+    ref = fx[case]
+    out = run_finalize(groups, ref.shape[0], normalize)
+    assert rel_err(out, ref) < 1e-5, case
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=1e-6)
+
+
+def test_factor_one_is_identity_and_clamped():
+    """bicubic at scale 1 is the identity: a lone 64x64 key comes back unchanged, negatives clamped."""
+    g = torch.Generator().manual_seed(1)
+    key = torch.randn(1, 77, 64, 64, generator=g).to(DEV)
+    grp = [_native.DaamKeyGroup(acc=key.data_ptr(), heads=1, h=64, w=64, tokens=77, head_sel=-1, reserved=0)]
+    out = run_finalize(grp, 77)
+    assert torch.equal(out, key[0].clamp(min=0))
+
+
+@pytest.mark.parametrize('h,x', [(32, 64), (16, 64), (8, 64), (48, 96), (24, 96), (32, 32)])
+def test_bicubic_matches_float64_math(h, x):
+    g = torch.Generator().manual_seed(h + x)
+    key = torch.exp(2.0 * torch.randn(2, 77, h, h, generator=g))
+    kd = key.to(DEV)
+    grp = [_native.DaamKeyGroup(acc=kd.data_ptr(), heads=2, h=h, w=h, tokens=77, head_sel=-1, reserved=0)]
+    out = run_finalize(grp, 20, x=x)
+    ref = O.math_global_heat_map([key[0].numpy(), key[1].numpy()], x, 20)
+    assert rel_err(out, ref) < 1e-5
+
+
+def test_finalize_rejects_empty_selection():
+    out = torch.empty(4, 64, 64, device=DEV)
+    with pytest.raises(_native.NativeError) as e:
+        _native.finalize([], 64, 4, False, out.data_ptr(), 0)
+    assert e.value.code == _native.E_INVALID
+
+
+def test_word_heat_map_and_expand_golden():
+    fx = golden('finalize')
+    tok = WhitespaceTokenizer()
+    g = torch.from_numpy(fx['global']).to(DEV)
+    ghm = GlobalHeatMap(tok, str(fx['prompt']), g)
+    w = ghm.compute_word_heat_map('three')
+    assert w.word == 'three' and w.heatmap.is_cuda
+    assert rel_err(w.heatmap, fx['word_three']) < 1e-6
+    multi = GlobalHeatMap(tok, 'red ball and red car', g).compute_word_heat_map('red')
+    assert rel_err(multi.value, fx['word_red_multi']) < 1e-6
+    by_idx = ghm.compute_word_heat_map('anything', word_idx=2)           # row 3 == 'three'
+    assert torch.equal(by_idx.heatmap, w.heatmap)
+    with pytest.raises(ValueError, match='Search word zebra not found in prompt!'):
+        ghm.compute_word_heat_map('zebra')
+    with pytest.raises(IndexError):
+        ghm.compute_word_heat_map('x', word_idx=40)
+    img = SimpleNamespace(size=(96, 80))
+    for case, kw, tol in [('expand', {}, 1e-5), ('expand_abs', {'absolute': True}, 1e-5)]:
+        got = w.expand_as(img, **kw)
+        assert not got.is_cuda and got.shape == (96, 80)
+        assert rel_err(got, fx[case]) < tol, case
+    thr = w.expand_as(img, threshold=0.4)
+    mism = (thr.numpy() != fx['expand_thr']).mean()
+    assert mism < 1e-3      # binarisation may flip pixels that sit within rounding of the threshold
+    assert w.compute_ioa(w) == pytest.approx(float((w.heatmap ** 2).sum() / w.heatmap.sum()), rel=1e-5)

@@ -1,0 +1,151 @@
+"""Host-side logic that needs no GPU: layer enumeration, hook plumbing, prompt/word bookkeeping, error behaviour."""
+import pytest
+import torch
+
+import daam_b200
+from daam_b200 import trace
+from daam_b200.build import build
+from daam_b200.hook import AggregateHooker, ObjectHooker, UNetCrossAttentionLocator
+from daam_b200.ops import cond_half
+from daam_b200.synthetic import (SD21_SPEC, SDXL_SPEC, TINY_SPEC, SDPAProcessor, SyntheticUNet, WhitespaceTokenizer,
+                                 make_pipeline)
+from daam_b200.utils import compute_token_merge_indices
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _built():
+    build()
+
+
+def meta_unet(spec):
+    with torch.device('meta'):
+        return SyntheticUNet(spec, body='skeleton')
+
+
+def test_export_surface():
+    for name in ['trace', 'set_seed', 'GlobalHeatMap', 'WordHeatMap', 'RawHeatMapCollection', 'ObjectHooker',
+                 'AggregateHooker', 'UNetCrossAttentionLocator', 'compute_token_merge_indices', 'auto_device',
+                 'auto_autocast', 'cache_dir', 'DiffusionHeatMapHooker']:
+        assert hasattr(daam_b200, name), name
+    assert daam_b200.trace is daam_b200.DiffusionHeatMapHooker
+
+
+def test_locator_sd21_order_and_names():
+    loc = UNetCrossAttentionLocator()
+    layers = loc.locate(meta_unet(SD21_SPEC))
+    assert len(layers) == 15
+    assert loc.layer_names == ['up-attn-0', 'up-attn-1', 'up-attn-2'] * 3 + ['down-attn-0', 'down-attn-1'] * 3
+    dims = [(l.to_q.in_features, l.heads) for l in layers]
+    assert dims == [(1280, 20)] * 3 + [(640, 10)] * 3 + [(320, 5)] * 3 + [(320, 5)] * 2 + [(640, 10)] * 2 + [(1280, 20)] * 2
+    loc_mid = UNetCrossAttentionLocator(locate_middle_block=True)
+    assert len(loc_mid.locate(meta_unet(SD21_SPEC))) == 16 and loc_mid.layer_names[-1] == 'mid-attn-0'
+    loc_low = UNetCrossAttentionLocator(restrict={0})
+    assert len(loc_low.locate(meta_unet(SD21_SPEC))) == 6
+    assert loc_low.layer_names == ['up-attn-0'] * 3 + ['down-attn-0'] * 3
+
+
+def test_locator_sdxl_counts():
+    unet = meta_unet(SDXL_SPEC)
+    assert len(UNetCrossAttentionLocator().locate(unet)) == 60
+    loc = UNetCrossAttentionLocator(locate_middle_block=True)
+    layers = loc.locate(unet)
+    assert len(layers) == 70
+    assert [l.heads for l in layers[:30]] == [20] * 30 and [l.heads for l in layers[30:36]] == [10] * 6
+    assert loc.layer_names[:3] == ['up-attn-0', 'up-attn-1', 'up-attn-2'] and loc.layer_names[29] == 'up-attn-29'
+
+
+def test_object_hooker_patch_and_restore():
+    class Target:
+        def greet(self, x):
+            return f'hi {x}'
+
+    class Hooker(ObjectHooker):
+        def _hook_impl(self):
+            self.monkey_patch('greet', self._greet)
+            self.monkey_patch('absent', self._greet, strict=False)
+
+        def _greet(hk, target, x):
+            return hk.monkey_super('greet', x).upper()
+
+    t = Target()
+    hk = Hooker(t)
+    with pytest.raises(RuntimeError, match='Module is not hooked'):
+        hk.unhook()
+    with hk:
+        assert t.greet('a') == 'HI A'
+        with pytest.raises(RuntimeError, match='Already hooked module'):
+            hk.hook()
+    assert t.greet('a') == 'hi a' and 'greet' not in vars(t) or t.greet('a') == 'hi a'
+
+    class Strict(ObjectHooker):
+        def _hook_impl(self):
+            self.monkey_patch('absent', lambda *_: None)
+
+    with pytest.raises(AttributeError):
+        Strict(t).hook()
+    agg = AggregateHooker([Hooker(Target()), Hooker(Target())])
+    with agg:
+        assert all(h.hooked for h in agg.module)
+    assert not any(h.hooked for h in agg.module)
+
+
+def test_token_merge_indices():
+    tok = WhitespaceTokenizer()
+    assert compute_token_merge_indices(tok, 'A dog and a Dog', 'dog') == ([2, 5], None)
+    assert compute_token_merge_indices(tok, 'a red ball', 'red ball') == ([2, 3], None)
+    assert compute_token_merge_indices(tok, 'a red ball', 'x', word_idx=4) == ([5], 4)
+    assert compute_token_merge_indices(tok, 'a red ball', 'ball', offset_idx=2) == ([5], None)
+    with pytest.raises(ValueError, match='Search word zebra not found in prompt!'):
+        compute_token_merge_indices(tok, 'a red ball', 'Zebra')
+
+
+def test_cond_half_rule():
+    assert cond_half(2, 5) == (1, 1, 0, 5)          # CFG pair: the conditional sample, all heads
+    assert cond_half(16, 10) == (8, 8, 0, 10)       # batched prompts: [uncond x 8, cond x 8]
+    assert cond_half(1, 8) == (0, 1, 4, 4)          # no guidance: the reference keeps the upper half of the heads
+    with pytest.raises(RuntimeError):
+        cond_half(3, 8)
+
+
+def test_trace_installs_and_restores_processors():
+    pipe = make_pipeline(TINY_SPEC)
+    layers = UNetCrossAttentionLocator().locate(pipe.unet)
+    check_inputs = pipe.check_inputs
+    tc = trace(pipe)
+    assert tc.latent_hw == 4096 and len(tc.layer_names) == 15
+    with tc:
+        assert all(l.processor is h for l, h in zip(layers, tc.module[:15]))
+        assert [h.layer_idx for h in tc.module[:15]] == list(range(15))
+        with pytest.raises(RuntimeError, match='No heat maps found. Did you forget to call'):
+            tc.compute_global_heat_map()
+        with pytest.raises(RuntimeError, match='No heat maps found for the given parameters.'):
+            tc.compute_global_heat_map(layer_idx=3)
+        with pytest.raises(ValueError, match='Only single prompt generation is supported'):
+            pipe(['a cat', 'a dog'], num_inference_steps=1)
+    assert all(isinstance(l.processor, SDPAProcessor) for l in layers)
+    assert pipe.check_inputs == check_inputs
+    tc.time_callback(0, 0, None)
+    assert tc.time_idx == 1
+
+
+def test_tracing_a_cpu_pipeline_fails_loudly():
+    pipe = make_pipeline(TINY_SPEC)
+    with trace(pipe, launch='layer') as tc:
+        with pytest.raises(RuntimeError, match='no CPU fallback'):
+            pipe('a cat', num_inference_steps=1)
+        tc.all_heat_maps.clear()
+
+
+def test_latent_hw_rule():
+    for sample, expect in [(64, 4096), (128, 4096), (96, 9216)]:
+        spec = TINY_SPEC.__class__(**{**TINY_SPEC.__dict__, 'sample_size': sample})
+        pipe = make_pipeline(spec)
+        assert trace(pipe).latent_hw == expect
+
+
+def test_unsupported_compat_options_are_explicit():
+    pipe = make_pipeline(TINY_SPEC)
+    with pytest.raises(NotImplementedError):
+        trace(pipe, save_heads=True)
+    with pytest.raises(ValueError):
+        trace(pipe, launch='sometimes')

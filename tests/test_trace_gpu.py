@@ -1,0 +1,154 @@
+"""End-to-end parity through the public API: `with trace(pipe) as tc: pipe(...); tc.compute_global_heat_map()` on the
+GPU vs the oracle fed the identical Q/K the hooks saw, and (loosely) vs the reference's own run of the same pipeline."""
+import numpy as np
+import pytest
+import torch
+
+from daam_b200 import _native, ops, trace
+from daam_b200.synthetic import TINY_SPEC, make_pipeline
+from oracle import daam_oracle as O
+from tests.util import golden, oracle_layer_maps, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+PROMPT = 'a dog chasing a red ball on the beach'
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32():
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+class Recorder:
+    """Wraps DiffusionHeatMapHooker._enqueue to keep CPU copies of every (layer, q, k) the hook handed to the kernel."""
+
+    def __init__(self, tc):
+        self.calls = []
+        inner = tc._enqueue
+
+        def enqueue(layer_idx, factor, q, k, heads, scale):
+            self.calls.append((layer_idx, factor, q.detach().float().cpu(), k.detach().float().cpu(), heads, scale))
+            return inner(layer_idx, factor, q, k, heads, scale)
+
+        tc._enqueue = enqueue
+
+    def oracle_store(self, prompt_idx=0):
+        store = O.OracleHeatMaps()
+        for layer_idx, factor, q, k, heads, scale in self.calls:
+            n = q.shape[0] // 2
+            pair = [prompt_idx, n + prompt_idx]
+            maps = O.port_layer_step(q[pair], k[pair], heads, scale)
+            for head, m in enumerate(maps):
+                store.update(factor, layer_idx, head, m)
+        return store
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.bfloat16, 4e-4), (torch.float16, 4e-4)])
+@pytest.mark.parametrize('launch', ['step', 'layer'])
+def test_pipeline_parity_with_oracle_on_identical_qk(dtype, tol, launch):
+    pipe = make_pipeline(TINY_SPEC, dtype=dtype, device=DEV, seed=3)
+    with trace(pipe, launch=launch) as tc:
+        rec = Recorder(tc)
+        pipe(PROMPT, num_inference_steps=3, generator=torch.Generator().manual_seed(11))
+        store = rec.oracle_store()
+        got = {k: v.clone() for k, v in tc.all_heat_maps}
+        assert set(got) == set(k for k, _ in store) and len(got) == 25
+        for key, ref in store:
+            assert rel_err(got[key], ref) < tol, key
+        n_tok = len(pipe.tokenizer.tokenize(PROMPT))
+        for kw in [{}, {'normalize': True}, {'factors': [1, 2]}, {'layer_idx': 9, 'head_idx': 0}, {'head_idx': 1}]:
+            ref = O.port_global_heat_map(store, 4096, n_tok, **kw)
+            out = tc.compute_global_heat_map(**kw).heat_maps
+            assert out.shape == ref.shape == (n_tok + 2, 64, 64)
+            assert rel_err(out, ref) < tol, kw
+        word = tc.compute_global_heat_map().compute_word_heat_map('ball')
+        ref_word = O.port_word_heat_map(O.port_global_heat_map(store, 4096, n_tok), pipe.tokenizer, PROMPT, 'ball')
+        assert rel_err(word.heatmap, ref_word) < tol
+    assert len(rec.calls) == 15 * 3
+
+
+def test_pipeline_against_reference_fixture():
+    """The reference's own run of this pipeline (CPU fp32) vs ours (GPU fp32): Q/K differ by GPU-vs-CPU matmul rounding
+    and by SDPA vs explicit softmax in the layer outputs, hence the loose 1e-3."""
+    fx = golden('pipeline_tiny')
+    pipe = make_pipeline(TINY_SPEC, dtype=torch.float32, device=DEV, seed=int(fx['unet_seed']))
+    with trace(pipe) as tc:
+        pipe(str(fx['prompt']), num_inference_steps=int(fx['steps']),
+             generator=torch.Generator().manual_seed(int(fx['gen_seed'])))
+        assert tc.layer_names == fx['layer_names'].tolist()
+        keys = sorted(k for k, _ in tc.all_heat_maps)
+        assert keys == sorted(tuple(k) for k in fx['keys'].tolist())
+        sums = {k: float(v.double().sum()) for k, v in tc.all_heat_maps}
+        for k, s in zip(fx['keys'].tolist(), fx['key_sums']):
+            assert abs(sums[tuple(k)] - s) < 1e-4 * s
+        assert rel_err(tc.compute_global_heat_map().heat_maps, fx['global']) < 1e-3
+        assert rel_err(tc.compute_global_heat_map(normalize=True).heat_maps, fx['global_norm']) < 1e-3
+        assert rel_err(tc.compute_global_heat_map(factors=[2]).heat_maps, fx['factors_2']) < 1e-3
+        assert rel_err(tc.compute_global_heat_map(layer_idx=9, head_idx=0).heat_maps, fx['layer9_head0']) < 1e-3
+        assert rel_err(tc.compute_global_heat_map().compute_word_heat_map('ball').heatmap, fx['word_ball']) < 1e-3
+
+
+def test_state_is_cleared_between_generations_and_trace_is_reusable():
+    pipe = make_pipeline(TINY_SPEC, dtype=torch.float16, device=DEV, seed=1)
+    with trace(pipe) as tc:
+        pipe('a cat', num_inference_steps=2, generator=torch.Generator().manual_seed(1))
+        first = tc.compute_global_heat_map().heat_maps.clone()
+        pipe('two small dogs', num_inference_steps=1, generator=torch.Generator().manual_seed(2))
+        assert tc.last_prompt == 'two small dogs'
+        second = tc.compute_global_heat_map().heat_maps.clone()
+        assert second.shape[0] == 5 and first.shape[0] == 4
+        pipe('a cat', num_inference_steps=2, generator=torch.Generator().manual_seed(1))
+        again = tc.compute_global_heat_map().heat_maps
+        assert torch.equal(first, again)              # accumulators were zeroed, not carried over
+        sums = [float(v.sum()) for _, v in tc.all_heat_maps]
+        assert all(abs(s - 2 * v.shape[-1] * v.shape[-2]) < 1e-2 * s for s, (_, v) in zip(sums, tc.all_heat_maps))
+    with pytest.raises(RuntimeError, match='Module is not hooked'):
+        tc.unhook()
+    out = pipe('a cat', num_inference_steps=1)          # un-hooked pipeline still runs (processors restored)
+    assert out.latents.shape[0] == 1
+
+
+def test_hooked_forward_output_matches_unhooked():
+    """The processor must not change what the UNet computes (it replaces the reference's explicit softmax with SDPA)."""
+    pipe = make_pipeline(TINY_SPEC, dtype=torch.float32, device=DEV, seed=5)
+    base = pipe('a cat on a mat', num_inference_steps=2, generator=torch.Generator().manual_seed(3)).latents
+    with trace(pipe):
+        hooked = pipe('a cat on a mat', num_inference_steps=2, generator=torch.Generator().manual_seed(3)).latents
+    assert rel_err(hooked, base) < 1e-5
+
+
+def test_batch_prompts_mode_equals_independent_traces():
+    pipe = make_pipeline(TINY_SPEC, dtype=torch.float16, device=DEV, seed=2)
+    prompts = ['a red ball', 'two dogs on the beach', 'a cat']
+    with trace(pipe, batch_prompts=True) as tc:
+        rec = Recorder(tc)
+        pipe(prompts, num_inference_steps=2, generator=torch.Generator().manual_seed(4))
+        assert tc.last_prompts == prompts
+        for i, p in enumerate(prompts):
+            store = rec.oracle_store(i)
+            n_tok = len(pipe.tokenizer.tokenize(p))
+            ref = O.port_global_heat_map(store, 4096, n_tok)
+            out = tc.compute_global_heat_map(prompt_idx=i).heat_maps
+            assert out.shape == ref.shape
+            assert rel_err(out, ref) < 4e-4, p
+            for (key, view), (rkey, rval) in zip(tc.all_heat_maps.items(i), store):
+                pass
+    with trace(pipe) as tc:
+        with pytest.raises(ValueError, match='Only single prompt generation is supported'):
+            pipe(prompts, num_inference_steps=1)
+
+
+def test_low_memory_and_mid_block_options():
+    pipe = make_pipeline(TINY_SPEC, dtype=torch.float16, device=DEV, seed=2)
+    with trace(pipe, low_memory=True) as tc:
+        pipe('a cat', num_inference_steps=1)
+        assert len(tc.layer_names) == 6 and len(list(tc.all_heat_maps)) == sum(h for h in (2, 2, 1, 1, 2, 2))
+    with trace(pipe, locate_middle_block=True) as tc:
+        pipe('a cat', num_inference_steps=1)
+        assert len(tc.layer_names) == 16
+        assert 15 not in tc.all_heat_maps.layers()      # the mid layer (factor 8) is located but never traced
+        assert tc.all_heat_maps.factors() == {1, 2, 4}
+        assert tc._gen_idx == 16
