@@ -88,12 +88,22 @@ def _check(rc: int):
         raise NativeError(rc, load().daam_last_error().decode('utf-8', 'replace'))
 
 
-def accumulate(layers: Sequence[DaamLayer], stream: int, flags: int = ACC_AUTO):
-    n = len(layers)
-    if n == 0:
+class PackedLayers:
+    """A ready-made ``daam_layer[]`` (host array) for call sites that replay the same layer calls."""
+
+    def __init__(self, layers: Sequence[DaamLayer]):
+        self.n = len(layers)
+        self.array = (DaamLayer * max(self.n, 1))(*layers)
+
+
+def accumulate(layers, stream: int, flags: int = ACC_AUTO):
+    """``layers``: a sequence of :class:`DaamLayer` or a :class:`PackedLayers`."""
+    packed = layers if isinstance(layers, PackedLayers) else PackedLayers(layers)
+    if packed.n == 0:
         return
-    arr = (DaamLayer * n)(*layers)
-    _check(load().daam_accumulate(arr, n, flags, ctypes.c_void_p(stream)))
+    rc = load().daam_accumulate(packed.array, packed.n, flags, stream)
+    if rc != 0:
+        _check(rc)
 
 
 def finalize(groups: Sequence[DaamKeyGroup], x: int, n_rows: int, normalize: bool, out_ptr: int, stream: int):

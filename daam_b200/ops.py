@@ -12,7 +12,7 @@ import torch
 
 from . import _native
 
-__all__ = ['cond_half', 'make_layer_desc', 'new_accumulator', 'accumulate', 'accumulate_layer']
+__all__ = ['cond_half', 'make_layer_desc', 'new_accumulator', 'pack', 'accumulate', 'accumulate_layer']
 
 _DTYPES = {torch.float32: _native.DAAM_F32, torch.float16: _native.DAAM_F16, torch.bfloat16: _native.DAAM_BF16}
 
@@ -63,12 +63,17 @@ def make_layer_desc(q: torch.Tensor, k: torch.Tensor, acc: torch.Tensor, heads: 
         dtype=_DTYPES[q.dtype], scale=float(scale), reserved=0)
 
 
-def accumulate(descs: Sequence[_native.DaamLayer], device, stream: Optional[torch.cuda.Stream] = None,
-               flags: int = _native.ACC_AUTO):
-    """Enqueue the fused kernel over the given layer calls on ``stream`` (default: the current stream)."""
+def pack(descs: Sequence[_native.DaamLayer]) -> _native.PackedLayers:
+    """Pre-build the host-side ``daam_layer[]`` once for layer calls that are replayed (bench loops, CUDA graphs)."""
+    return _native.PackedLayers(list(descs))
+
+
+def accumulate(descs, device, stream: Optional[torch.cuda.Stream] = None, flags: int = _native.ACC_AUTO):
+    """Enqueue the fused kernel over the given layer calls (sequence of descriptors or :func:`pack` result) on
+    ``stream`` (default: the current stream of ``device``)."""
     with torch.cuda.device(device):
         s = torch.cuda.current_stream(device) if stream is None else stream
-        _native.accumulate(list(descs), s.cuda_stream, flags)
+        _native.accumulate(descs, s.cuda_stream, flags)
 
 
 def accumulate_layer(q: torch.Tensor, k: torch.Tensor, heads: int, scale: Optional[float] = None,

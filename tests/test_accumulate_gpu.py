@@ -19,8 +19,16 @@ TOL = {torch.float32: 1e-5, torch.float16: 2e-4, torch.bfloat16: 2e-4}
 PATHS = [
     ('simt-ldst', _native.ACC_FORCE_SIMT | _native.ACC_RMW_LDST),
     ('simt-red', _native.ACC_FORCE_SIMT | _native.ACC_RMW_RED),
+    ('mma-red', _native.ACC_FORCE_MMA | _native.ACC_RMW_RED),
+    ('mma-ldst', _native.ACC_FORCE_MMA | _native.ACC_RMW_LDST),
     ('auto', _native.ACC_AUTO),
 ]
+
+
+def skip_unless_mma_applies(path, dtype, head_dim):
+    """The tcgen05 kernel takes 16-bit projections with head_dim 64; forcing it elsewhere is an error by design."""
+    if path.startswith('mma') and (dtype == torch.float32 or head_dim != 64):
+        pytest.skip('tcgen05 path: 16-bit inputs with head_dim 64 only')
 
 
 def assert_close(got, ref, tol, what=''):
@@ -39,6 +47,7 @@ def test_golden_layers(name, dtype, path, flags):
     q = torch.from_numpy(fx['q']).to(DEV, dtype)
     k = torch.from_numpy(fx['k']).to(DEV, dtype)
     heads = int(fx['heads'])
+    skip_unless_mma_applies(path, dtype, int(fx['head_dim']))
     acc = ops.accumulate_layer(q, k, heads, float(fx['scale']), flags=flags)
     torch.cuda.synchronize()
     ref = torch.from_numpy(fx['maps']).reshape(1, heads, 77, -1)
@@ -72,6 +81,7 @@ def test_seeded_shapes_vs_oracle(hw, heads, d, dtype):
 def test_time_accumulation_and_linearity(dtype, path, flags):
     """acc is a running sum over steps (daam/heatmap.py:153-156): 3 different steps, then the same step twice more."""
     hw, heads, d = 1024, 4, 64
+    skip_unless_mma_applies(path, dtype, d)
     g = torch.Generator().manual_seed(5)
     acc = ops.new_accumulator(1, heads, hw, DEV)
     ref = torch.zeros(heads, 77, hw)
@@ -195,6 +205,30 @@ def test_invalid_arguments_are_rejected():
         ops.make_layer_desc(q, torch.randn(2, 77, 128, device=DEV), ops.new_accumulator(1, 3, 64, DEV), 2, 0.125)
     with pytest.raises(RuntimeError, match='CUDA tensors only'):
         ops.make_layer_desc(q.cpu(), k76.cpu(), acc, 2, 0.125)
+
+
+def test_forcing_tcgen05_on_unsupported_input_is_an_error():
+    q = torch.randn(2, 64, 128, device=DEV)
+    k = torch.randn(2, 77, 128, device=DEV)
+    with pytest.raises(_native.NativeError) as e:
+        ops.accumulate_layer(q, k, 2, flags=_native.ACC_FORCE_MMA)
+    assert e.value.code == _native.E_UNSUPPORTED
+
+
+@pytest.mark.parametrize('mode', [_native.ACC_RMW_RED, _native.ACC_RMW_LDST])
+def test_tcgen05_partial_and_tiny_tiles(mode):
+    """hw not a multiple of the 128-pixel tile (576 = 4.5 tiles, 144, 16): TMA zero-fills the tail rows and clips the
+    reduce; nothing outside the head's [77, hw] slab may be touched (guard rows before/after stay zero)."""
+    for hw, heads in [(576, 3), (144, 2), (16, 2), (2304, 2)]:
+        g = torch.Generator().manual_seed(hw)
+        q = torch.randn(2, hw, heads * 64, generator=g).half().to(DEV)
+        k = torch.randn(2, 77, heads * 64, generator=g).half().to(DEV)
+        slab = torch.zeros(heads + 2, 77, hw, device=DEV)
+        acc = slab[1:-1].unsqueeze(0)
+        ops.accumulate([ops.make_layer_desc(q, k, acc, heads, 0.125)], DEV, flags=_native.ACC_FORCE_MMA | mode)
+        torch.cuda.synchronize()
+        assert_close(acc[0], oracle_layer_maps(q, k, heads, 0.125), TOL[torch.float16], f'hw {hw}')
+        assert float(slab[0].abs().max()) == 0.0 and float(slab[-1].abs().max()) == 0.0
 
 
 def test_full_size_sd21_step_properties():

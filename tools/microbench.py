@@ -18,14 +18,14 @@ from daam_b200 import _native, ops  # noqa: E402
 def time_variant(sets, flags, per_layer, steps=200, warmup=20):
     stream = torch.cuda.current_stream()
     n = len(sets)
+    singles = [[ops.pack([s[0].array[j]]) for j in range(s[0].n)] for s in sets] if per_layer else None
 
     def step(i):
-        descs = sets[i % n][0]
         if per_layer:
-            for d in descs:
-                ops.accumulate([d], 'cuda', stream, flags)
+            for d in singles[i % n]:
+                ops.accumulate(d, 'cuda', stream, flags)
         else:
-            ops.accumulate(descs, 'cuda', stream, flags)
+            ops.accumulate(sets[i % n][0], 'cuda', stream, flags)
 
     for i in range(warmup):
         step(i)
