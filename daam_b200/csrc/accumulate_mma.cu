@@ -195,6 +195,11 @@ __global__ void __launch_bounds__(kThreads, 2) accumulate_mma_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation) may overlap the tail of the
+  // previous kernel on the stream; nothing below (TMA loads, reduce-adds) may start before that kernel has completed
+  // and flushed. Our own dependents may be scheduled as soon as every CTA of this grid is past this point.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 4) {
     // ===== TMA producer =====
@@ -423,7 +428,17 @@ int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStre
   }
   int grid = dev.sm_count * 2;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  accumulate_mma_kernel<<<grid, kThreads, kSmemBytes, stream>>>(mp);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = p.pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel, mp));
   DAAM_CUDA_TRY(cudaGetLastError());
   count_launch();
   return DAAM_OK;

@@ -35,7 +35,7 @@ struct LaunchParams {
   int n_layers;
   int total_tiles;
   int rmw_mode;             // 0: load/add/store, 1: reduce-add
-  int pad_;
+  int pdl;                  // 1: launch with programmatic stream serialization (prologue overlaps the previous kernel)
   LayerParams layer[kMaxLayersPerLaunch];
 };
 

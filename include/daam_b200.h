@@ -42,9 +42,11 @@ enum daam_dtype { DAAM_F32 = 0, DAAM_F16 = 1, DAAM_BF16 = 2 };
 #define DAAM_ACC_FORCE_SIMT  1u  /* always the SIMT fp32 ("warp dot") kernel */
 #define DAAM_ACC_FORCE_MMA   2u  /* tcgen05 kernel or DAAM_E_UNSUPPORTED */
 #define DAAM_ACC_RMW_MASK   0x30u
-#define DAAM_ACC_RMW_AUTO   0x00u
+#define DAAM_ACC_RMW_AUTO   0x00u /* = RED on both paths (measured faster; one add per element per launch, so
+                                     results stay deterministic) */
 #define DAAM_ACC_RMW_LDST   0x10u /* coalesced load / add / store of the accumulator tile */
 #define DAAM_ACC_RMW_RED    0x20u /* red.global.add.f32 (SIMT) / bulk-async reduce-add from shared memory (MMA) */
+#define DAAM_ACC_NO_PDL     0x100u /* launch without programmatic dependent launch (measurement / debugging) */
 
 /*
  * One traced cross-attention layer call: the conditional half of the projections `to_q(hidden_states)` and

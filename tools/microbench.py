@@ -53,6 +53,7 @@ def main():
         'simt-red': _native.ACC_FORCE_SIMT | _native.ACC_RMW_RED,
         'mma-red': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED,
         'mma-ldst': _native.ACC_FORCE_MMA | _native.ACC_RMW_LDST,
+        'mma-red-nopdl': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED | _native.ACC_NO_PDL,
     }
     if args.variants:
         variants = {k: v for k, v in variants.items() if k in args.variants}
