@@ -214,17 +214,19 @@ def leg_value(args, layers, dtype, D: Dist, windows):
     return ms, launches, n_sets
 
 
-def leg_e2e(args, spec, dtype, D: Dist, windows):
-    """Public API on the cross-attention skeleton: host-resident pipeline inputs, H2D/D2H every step."""
+def leg_e2e(args, spec, dtype, D: Dist, windows, cuda_graph=True):
+    """Public API on the cross-attention skeleton: host-resident pipeline inputs, H2D/D2H every step. With
+    ``cuda_graph`` the pipeline replays the step's device work (UNet + the tracer's kernel) from a CUDA graph."""
     from daam_b200 import trace
     from daam_b200.distributed import gather_heat_maps
     from daam_b200.synthetic import make_pipeline
-    pipe = make_pipeline(spec, body='skeleton', dtype=dtype, device='cuda', seed=D.rank, init_on_device=True)
+    pipe = make_pipeline(spec, body='skeleton', dtype=dtype, device='cuda', seed=D.rank, init_on_device=True,
+                         cuda_graph=cuda_graph)
     prompts = ['a photo of a dog chasing a red ball on the beach at sunset'] * args.prompts
     prompt_arg = prompts[0] if args.prompts == 1 else prompts
     out_h = None
     with trace(pipe, batch_prompts=args.prompts > 1) as tc:
-        pipe(prompt_arg, num_inference_steps=max(1, args.warmup))
+        pipe(prompt_arg, num_inference_steps=max(3, args.warmup))     # also captures the step graph
         tc.compute_global_heat_map()
         torch.cuda.synchronize()
         D.barrier()
@@ -284,9 +286,42 @@ def leg_hook_overhead(args, spec, dtype, windows):
                 res[mode] = run(n)
                 tc.synchronize()
         base2 = run(n)
+        # the same comparison with the forward replayed from a CUDA graph (no host launch cost on either side)
+        def graphed():
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                pipe.unet(lat, 500.0, emb)
+            ts = []
+            for _ in range(3):
+                g.replay()
+            for _ in range(n):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                g.replay()
+                b.record()
+                ts.append((a, b))
+            torch.cuda.synchronize()
+            ts = sorted(a.elapsed_time(b) for a, b in ts)
+            return ts[len(ts) // 2]
+
+        gres = {}
+        try:
+            gres['unhooked'] = graphed()
+            with trace(pipe) as tc:
+                run(2)                       # eager steps allocate the slabs before capture
+                gres['hooked'] = graphed()
+                tc.synchronize()
+        except Exception as e:
+            gres['error'] = repr(e)
     windows.append((t0, time.time()))
     base = min(base, base2)
-    return {'unhooked_ms_per_step': round(base, 4),
+    graph = {}
+    if 'hooked' in gres:
+        graph = {'graph_unhooked_ms_per_step': round(gres['unhooked'], 4), 'graph_hooked_ms_per_step': round(gres['hooked'], 4),
+                 'graph_overhead_pct': round(100 * (gres['hooked'] - gres['unhooked']) / gres['unhooked'], 3)}
+    elif 'error' in gres:
+        graph = {'graph_error': gres['error']}
+    return {**graph, 'unhooked_ms_per_step': round(base, 4),
             'hooked_ms_per_step': round(res['step'], 4), 'overhead_ms_per_step': round(res['step'] - base, 4),
             'overhead_pct': round(100 * (res['step'] - base) / base, 3),
             'hooked_layer_mode_ms_per_step': round(res['layer'], 4),
@@ -426,7 +461,8 @@ def main():
 
     with torch.no_grad():
         ms, launches, n_sets = leg_value(args, layers, dtype, D, windows)
-        e2e_ms, h2d, d2h = leg_e2e(args, spec, dtype, D, windows)
+        e2e_ms, h2d, d2h = leg_e2e(args, spec, dtype, D, windows, cuda_graph=True)
+        eager_ms, _, _ = leg_e2e(args, spec, dtype, D, windows, cuda_graph=False)
         overhead = None
         if not args.skip_overhead and D.rank == 0 and D.world == 1:
             try:
@@ -462,9 +498,11 @@ def main():
         'clocks': clocks,
         'e2e': {'value': px * args.steps * n / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps,
+                'eager_value': px * args.steps * n / (eager_ms * 1e-3), 'eager_ms_per_step': eager_ms / args.steps,
                 'what': 'with trace(pipe): pipe(prompt, K steps) on the cross-attn skeleton UNet (to_q/to_k/to_v, SDPA, '
                         'to_out + fused heat-map kernel), pinned-host inputs H2D every step, + compute_global_heat_map '
-                        '(+ all_gather when N>1) + D2H of the maps'},
+                        '(+ all_gather when N>1) + D2H of the maps; the pipeline replays the step from a CUDA graph '
+                        '(eager_*: same without graph replay, host-launch bound)'},
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                      'traffic': recorded_traffic(args.workload), 'kernel': 'daam accumulate (softmax(QK^T)->unravel->+=)',

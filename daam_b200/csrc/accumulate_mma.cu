@@ -433,9 +433,12 @@ int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStre
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
+  // Inside a stream capture the launch becomes a plain kernel node (programmatic edges are left to the graph owner).
+  cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+  DAAM_CUDA_TRY(cudaStreamIsCapturing(stream, &capture));
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = p.pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (p.pdl && capture == cudaStreamCaptureStatusNone) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel, mp));

@@ -82,6 +82,9 @@ class RawHeatMapCollection:
         shape = (n_prompts, heads, _native.TOKENS, h * w)
         if slab is None or tuple(slab.acc.shape) != shape or slab.acc.device != torch.device(device) \
                 or slab.factor != factor:
+            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                raise RuntimeError('accumulator slabs cannot be created inside a CUDA-graph capture: run one eager '
+                                   'UNet step under trace() before capturing')
             acc = torch.zeros(shape, dtype=torch.float32, device=device)
             slab = LayerSlab(layer_idx, factor, heads, h, w, acc, head_offset=head_offset)
             self.slabs[layer_idx] = slab
@@ -89,6 +92,11 @@ class RawHeatMapCollection:
             slab.touched = True
             self._order.append(layer_idx)
         return slab
+
+    def mark_live(self, slab: LayerSlab):
+        if not slab.touched:
+            slab.touched = True
+            self._order.append(slab.layer_idx)
 
     # -- reference interface ------------------------------------------------------------------------------------------
     def update(self, factor: int, layer_idx: int, head_idx: int, heatmap: torch.Tensor):

@@ -71,9 +71,14 @@ def pack(descs: Sequence[_native.DaamLayer]) -> _native.PackedLayers:
 def accumulate(descs, device, stream: Optional[torch.cuda.Stream] = None, flags: int = _native.ACC_AUTO):
     """Enqueue the fused kernel over the given layer calls (sequence of descriptors or :func:`pack` result) on
     ``stream`` (default: the current stream of ``device``)."""
-    with torch.cuda.device(device):
-        s = torch.cuda.current_stream(device) if stream is None else stream
+    dev = device if isinstance(device, torch.device) else torch.device(device)
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    s = torch.cuda.current_stream(index) if stream is None else stream
+    if index == torch.cuda.current_device():
         _native.accumulate(descs, s.cuda_stream, flags)
+    else:
+        with torch.cuda.device(index):
+            _native.accumulate(descs, s.cuda_stream, flags)
 
 
 def accumulate_layer(q: torch.Tensor, k: torch.Tensor, heads: int, scale: Optional[float] = None,

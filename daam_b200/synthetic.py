@@ -399,20 +399,28 @@ class _ImageProcessor:
 class SyntheticPipeline:
     """A StableDiffusionPipeline-shaped driver around :class:`SyntheticUNet`.
 
-    Per denoising step it copies the step's inputs (latents, text embeddings, both kept in pinned host memory when the
-    UNet lives on a GPU) to the device, runs the UNet on the CFG batch ``[uncond x N, cond x N]`` and reads the guided
-    noise estimate's mean back to the host -- the host<->device traffic ``bench.py`` counts for its ``e2e`` figure.
+    Per denoising step it copies the step's inputs (latents, text embeddings, timestep; kept in pinned host memory when
+    the UNet lives on a GPU) to the device, runs the UNet on the CFG batch ``[uncond x N, cond x N]`` and reads the
+    guided noise estimate's mean back to the host -- the host<->device traffic ``bench.py`` counts for its ``e2e`` figure.
+
+    ``cuda_graph=True`` replays the step's device work (UNet forward + guidance update) from a CUDA graph: the first step
+    of a configuration runs eagerly, the second is captured, later steps and later calls replay it. Attention processors
+    installed at capture time (e.g. a tracer's) are part of the graph; the graph is re-captured when they change.
     """
 
-    def __init__(self, unet: SyntheticUNet, dtype=torch.float32, device='cpu', seed: int = 0):
+    def __init__(self, unet: SyntheticUNet, dtype=torch.float32, device='cpu', seed: int = 0,
+                 cuda_graph: bool = False):
         self.unet = unet.to(device=device, dtype=dtype).eval()
         self.dtype, self.device = dtype, torch.device(device)
         self.vae_scale_factor = 8
         self.tokenizer = WhitespaceTokenizer()
         self.image_processor = _ImageProcessor()
         self.seed = seed
+        self.cuda_graph = cuda_graph and self.device.type == 'cuda'
         self.h2d_bytes_per_step = 0
         self.d2h_bytes_per_step = 0
+        self._graphs = {}
+        self._attn = [m for m in self.unet.modules() if isinstance(m, SyntheticAttention)]
 
     def check_inputs(self, prompt, *args, **kwargs):
         if not isinstance(prompt, (str, list)):
@@ -423,6 +431,34 @@ class SyntheticPipeline:
         n, spec = len(prompts), self.unet.spec
         emb = torch.randn(2 * n, spec.tokens, spec.cross_attention_dim, generator=generator, dtype=torch.float32)
         return emb
+
+    def _step(self, st, guidance_scale):
+        """Device work of one denoising step on the static buffers ``st``."""
+        lat, n = st['latents'], st['latents'].shape[0]
+        eps = self.unet(torch.cat([lat, lat], dim=0), st['t'], st['emb'])
+        eps_u, eps_c = eps[:n], eps[n:]
+        eps = eps_u + guidance_scale * (eps_c - eps_u)
+        lat.copy_((lat - 0.02 * eps).clamp_(-4, 4))
+        st['stat'].copy_(eps.float().mean(dim=(1, 2, 3)))
+
+    def _state(self, n):
+        spec, dev = self.unet.spec, self.device
+        key = (n, tuple(id(m.processor) for m in self._attn))
+        st = self._graphs.get(key)
+        if st is None:
+            if len(self._graphs) > 4:
+                self._graphs.clear()
+            st = {
+                'emb': torch.empty(2 * n, spec.tokens, spec.cross_attention_dim, dtype=self.dtype, device=dev),
+                'lat0': torch.empty(n, spec.in_channels, spec.sample_size, spec.sample_size, dtype=self.dtype, device=dev),
+                'latents': torch.empty(n, spec.in_channels, spec.sample_size, spec.sample_size, dtype=self.dtype,
+                                       device=dev),
+                't': torch.zeros(1, dtype=torch.float32, device=dev),
+                'stat': torch.zeros(n, dtype=torch.float32, device=dev),
+                'graph': None, 'eager_steps': 0,
+            }
+            self._graphs[key] = st
+        return st
 
     @torch.no_grad()
     def __call__(self, prompt, num_inference_steps: int = 50, generator: Optional[torch.Generator] = None,
@@ -436,33 +472,41 @@ class SyntheticPipeline:
         emb_h = self.encode(prompts, generator).to(self.dtype)
         lat_h = torch.randn(n, spec.in_channels, spec.sample_size, spec.sample_size, generator=generator,
                             dtype=torch.float32).to(self.dtype)
+        t_h = torch.tensor([[1000.0 * (1.0 - i / max(1, num_inference_steps))] for i in range(num_inference_steps)])
+        out_h = torch.empty(n, dtype=torch.float32)
         if cuda:
-            emb_h, lat_h = emb_h.pin_memory(), lat_h.pin_memory()
-            out_h = torch.empty(n, dtype=torch.float32).pin_memory()
-        self.h2d_bytes_per_step = emb_h.numel() * emb_h.element_size() + lat_h.numel() * lat_h.element_size()
+            emb_h, lat_h, t_h, out_h = emb_h.pin_memory(), lat_h.pin_memory(), t_h.pin_memory(), out_h.pin_memory()
+        self.h2d_bytes_per_step = emb_h.numel() * emb_h.element_size() + lat_h.numel() * lat_h.element_size() + 4
         self.d2h_bytes_per_step = n * 4
-        latents = None
+        st = self._state(n)
         for i in range(num_inference_steps):
-            emb = emb_h.to(self.device, non_blocking=True)
-            lat0 = lat_h.to(self.device, non_blocking=True)
-            latents = lat0 if latents is None else latents
-            t = 1000.0 * (1.0 - i / max(1, num_inference_steps))
-            eps = self.unet(torch.cat([latents, latents], dim=0), t, emb)
-            eps_u, eps_c = eps[:n], eps[n:]
-            eps = eps_u + guidance_scale * (eps_c - eps_u)
-            latents = (latents - 0.02 * eps).clamp_(-4, 4)
-            stat = eps.float().mean(dim=(1, 2, 3))
-            if cuda:
-                out_h.copy_(stat, non_blocking=True)
+            st['emb'].copy_(emb_h, non_blocking=True)            # H2D: the step's inputs
+            st['lat0'].copy_(lat_h, non_blocking=True)
+            st['t'].copy_(t_h[i], non_blocking=True)
+            if i == 0:
+                st['latents'].copy_(st['lat0'])
+            if self.cuda_graph and st['graph'] is not None:
+                st['graph'].replay()
+            elif self.cuda_graph and st['eager_steps'] >= 1:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._step(st, guidance_scale)
+                st['graph'] = graph
+                graph.replay()                                     # capture does not execute: run the step now
+            else:
+                self._step(st, guidance_scale)
+                st['eager_steps'] += 1
+            out_h.copy_(st['stat'], non_blocking=True)           # D2H: the step's result
             if callback is not None:
-                callback(i, t, latents)
+                callback(i, float(t_h[i]), st['latents'])
+        latents = st['latents'].clone()
         image = latents[:, :3].float()
         images = self.image_processor.postprocess(image, output_type='pil')
         return SimpleNamespace(images=images, latents=latents)
 
 
 def make_pipeline(spec: UNetSpec = SD21_SPEC, body: str = 'skeleton', dtype=torch.float32, device='cpu',
-                  seed: int = 0, init_on_device: bool = False) -> SyntheticPipeline:
+                  seed: int = 0, init_on_device: bool = False, cuda_graph: bool = False) -> SyntheticPipeline:
     """Random-init pipeline. Weights are drawn on the CPU from ``seed`` (identical on every box) unless
     ``init_on_device`` (fast for the full-size bodies; values then depend on the device RNG)."""
     gen_state = torch.random.get_rng_state()
@@ -473,4 +517,4 @@ def make_pipeline(spec: UNetSpec = SD21_SPEC, body: str = 'skeleton', dtype=torc
     else:
         unet = SyntheticUNet(spec, body=body)
     torch.random.set_rng_state(gen_state)
-    return SyntheticPipeline(unet, dtype=dtype, device=device, seed=seed)
+    return SyntheticPipeline(unet, dtype=dtype, device=device, seed=seed, cuda_graph=cuda_graph)

@@ -68,6 +68,7 @@ class DiffusionHeatMapHooker(AggregateHooker):
         self.kernel_flags = kernel_flags
         self._pending: List[tuple] = []        # (layer_idx, DaamLayer, q, k, acc) awaiting the step launch
         self._pending_layers = set()
+        self._desc_cache: Dict[int, tuple] = {}
         self._stream: Optional[torch.cuda.Stream] = None
         self._dirty = False                    # side-stream work not yet ordered before the current stream
         self.all_heat_maps.bind(self.synchronize, self._zero_slabs)
@@ -94,8 +95,19 @@ class DiffusionHeatMapHooker(AggregateHooker):
         raise NotImplementedError('GenerationExperiment persistence (reference daam/experiment.py) is outside the '
                                   'hot-path scope; use compute_global_heat_map().heat_maps')
 
+    def _hook_impl(self):
+        super()._hook_impl()
+        unet = self.pipe.unet
+        self._forward_hook = None
+        if self.launch == 'step' and hasattr(unet, 'register_forward_hook'):
+            # end of every UNet forward = end of the step's layer calls: issue the step launch right away
+            self._forward_hook = unet.register_forward_hook(lambda *_: self.flush())
+
     def _unhook_impl(self):
         self.flush()
+        if getattr(self, '_forward_hook', None) is not None:
+            self._forward_hook.remove()
+            self._forward_hook = None
         super()._unhook_impl()
 
     # -- kernel queue -------------------------------------------------------------------------------------------------
@@ -106,25 +118,36 @@ class DiffusionHeatMapHooker(AggregateHooker):
 
     def _enqueue(self, layer_idx: int, factor: int, q: torch.Tensor, k: torch.Tensor, heads: int, scale: float):
         """Register one traced layer call: ``q [B, hw, C]``, ``k [B, 77, C]`` straight from ``to_q`` / ``to_k``."""
-        if not q.is_cuda:
-            raise RuntimeError('daam_b200 traces pipelines that live on a CUDA device only (there is no CPU fallback)')
-        bsz, hw, _ = q.shape
-        side = int(math.sqrt(hw))
-        if side * side != hw:
-            raise RuntimeError(f'layer {layer_idx}: {hw} query positions are not a square map')
+        if layer_idx in self._pending_layers:   # the layer comes round again: a new UNet forward has started
+            self.flush()
         if q.stride(-1) != 1 or k.stride(-1) != 1:
             q, k = q.contiguous(), k.contiguous()
-        # "second half of the batch*heads axis" (trace.py:240): the conditional samples of a CFG batch
-        _, n_prompts, head0, n_heads = ops.cond_half(bsz, heads)
-        if n_prompts > 1 and not self.batch_prompts:
-            raise ValueError('Only single prompt generation is supported for heat map computation.')
-        slab = self.all_heat_maps.slab_for(layer_idx, factor, n_prompts, n_heads, side, side, q.device, head0)
-        desc = ops.make_layer_desc(q, k, slab.acc, heads, scale)
+        # Steady state: same shapes/strides as the last call of this layer -> only the two data pointers change.
+        sig = (q.shape, q.stride(), k.shape, k.stride(), q.dtype, q.device, heads, factor)
+        cached = self._desc_cache.get(layer_idx)
+        if cached is not None and cached[0] == sig and self.all_heat_maps.slabs.get(layer_idx) is cached[2]:
+            _, desc, slab, q_off, k_off = cached
+            desc.q = q.data_ptr() + q_off
+            desc.k = k.data_ptr() + k_off
+            self.all_heat_maps.mark_live(slab)
+        else:
+            if not q.is_cuda:
+                raise RuntimeError('daam_b200 traces pipelines that live on a CUDA device only (there is no CPU '
+                                   'fallback)')
+            bsz, hw, _ = q.shape
+            side = int(math.sqrt(hw))
+            if side * side != hw:
+                raise RuntimeError(f'layer {layer_idx}: {hw} query positions are not a square map')
+            # "second half of the batch*heads axis" (trace.py:240): the conditional samples of a CFG batch
+            _, n_prompts, head0, n_heads = ops.cond_half(bsz, heads)
+            if n_prompts > 1 and not self.batch_prompts:
+                raise ValueError('Only single prompt generation is supported for heat map computation.')
+            slab = self.all_heat_maps.slab_for(layer_idx, factor, n_prompts, n_heads, side, side, q.device, head0)
+            desc = ops.make_layer_desc(q, k, slab.acc, heads, scale)
+            self._desc_cache[layer_idx] = (sig, desc, slab, desc.q - q.data_ptr(), desc.k - k.data_ptr())
         if self.launch == 'layer':
             ops.accumulate([desc], q.device, flags=self.kernel_flags)
             return
-        if layer_idx in self._pending_layers:   # the layer comes round again: a new UNet forward has started
-            self.flush()
         self._pending.append((layer_idx, desc, q, k, slab.acc))   # tensors kept alive until the launch
         self._pending_layers.add(layer_idx)
 
@@ -133,15 +156,20 @@ class DiffusionHeatMapHooker(AggregateHooker):
         if not self._pending:
             return
         device = self._pending[0][2].device
-        side = self._side_stream(device)
-        side.wait_stream(torch.cuda.current_stream(device))       # Q/K were produced on the current stream
-        ops.accumulate([p[1] for p in self._pending], device, stream=side, flags=self.kernel_flags)
-        for _, _, q, k, _ in self._pending:                            # keep the projections alive until the kernel ran
-            q.record_stream(side)
-            k.record_stream(side)
+        descs = [p[1] for p in self._pending]
+        if torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture of the UNet step: the launch becomes a node of the captured stream itself
+            ops.accumulate(descs, device, flags=self.kernel_flags)
+        else:
+            side = self._side_stream(device)
+            side.wait_stream(torch.cuda.current_stream(device))   # Q/K were produced on the current stream
+            ops.accumulate(descs, device, stream=side, flags=self.kernel_flags)
+            for _, _, q, k, _ in self._pending:                     # keep the projections alive until the kernel ran
+                q.record_stream(side)
+                k.record_stream(side)
+            self._dirty = True
         self._pending.clear()
         self._pending_layers.clear()
-        self._dirty = True
 
     def synchronize(self):
         """Make every accumulate issued so far visible to work enqueued on the current stream afterwards."""

@@ -152,3 +152,26 @@ def test_low_memory_and_mid_block_options():
         assert 15 not in tc.all_heat_maps.layers()      # the mid layer (factor 8) is located but never traced
         assert tc.all_heat_maps.factors() == {1, 2, 4}
         assert tc._gen_idx == 16
+
+
+@pytest.mark.parametrize('launch', ['step', 'layer'])
+def test_cuda_graph_replay_traces_like_eager(launch):
+    """The tracer's kernels become nodes of a captured UNet step: graph replays must accumulate exactly like eager."""
+    prompt = 'a dog chasing a red ball'
+    eager_pipe = make_pipeline(TINY_SPEC, dtype=torch.float16, device=DEV, seed=4)
+    graph_pipe = make_pipeline(TINY_SPEC, dtype=torch.float16, device=DEV, seed=4, cuda_graph=True)
+    with trace(eager_pipe, launch=launch) as tc:
+        eager_pipe(prompt, num_inference_steps=5, generator=torch.Generator().manual_seed(9))
+        ref = tc.compute_global_heat_map().heat_maps.clone()
+        ref_keys = {k: v.clone() for k, v in tc.all_heat_maps}
+    with trace(graph_pipe, launch=launch) as tc:
+        for _ in range(2):    # second generation replays the cached graph from step 0
+            graph_pipe(prompt, num_inference_steps=5, generator=torch.Generator().manual_seed(9))
+            got = tc.compute_global_heat_map().heat_maps
+            assert rel_err(got, ref) < 2e-3          # eager vs graph: cuBLAS may pick other algorithms under capture
+            for k, v in tc.all_heat_maps:
+                s = float(v.double().sum())
+                assert abs(s - 5 * v.shape[-1] * v.shape[-2]) < 1e-3 * s, k     # exactly 5 steps were accumulated
+        assert any(st['graph'] is not None for st in graph_pipe._graphs.values())
+    base = graph_pipe(prompt, num_inference_steps=3)     # un-hooked: new processors -> new graph, still runs
+    assert base.latents.shape[0] == 1
