@@ -49,6 +49,7 @@ class LayerSlab:
     acc: torch.Tensor            # fp32 [n_prompts, heads, 77, h*w]
     touched: bool = False        # a key exists only once it has been updated (defaultdict semantics)
     head_offset: int = 0         # first real head behind key head 0 (non-zero only for the un-guided B=1 quirk)
+    captured: bool = False       # the layer's kernel launch is part of a CUDA graph: replays update it without the hook
 
     @property
     def n_prompts(self) -> int:
@@ -151,9 +152,9 @@ class RawHeatMapCollection:
         else:
             for slab in live:
                 slab.acc.zero_()
-        for slab in live:
-            slab.touched = False
-        self._order.clear()
+        for slab in live:                     # graph-captured layers stay live: replays bypass the Python hook
+            slab.touched = slab.captured
+        self._order = [i for i in self._order if self.slabs[i].captured]
 
 
 class WordHeatMap:

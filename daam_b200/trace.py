@@ -145,6 +145,8 @@ class DiffusionHeatMapHooker(AggregateHooker):
             slab = self.all_heat_maps.slab_for(layer_idx, factor, n_prompts, n_heads, side, side, q.device, head0)
             desc = ops.make_layer_desc(q, k, slab.acc, heads, scale)
             self._desc_cache[layer_idx] = (sig, desc, slab, desc.q - q.data_ptr(), desc.k - k.data_ptr())
+        if torch.cuda.is_current_stream_capturing():
+            slab.captured = True
         if self.launch == 'layer':
             ops.accumulate([desc], q.device, flags=self.kernel_flags)
             return
