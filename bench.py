@@ -262,13 +262,14 @@ def leg_hook_overhead(args, spec, dtype, windows):
     spec_ = pipe.unet.spec
     lat = torch.randn(2, spec_.in_channels, spec_.sample_size, spec_.sample_size, device='cuda', dtype=dtype)
     emb = torch.randn(2, spec_.tokens, spec_.cross_attention_dim, device='cuda', dtype=dtype)
+    t_dev = torch.full((1,), 500.0, device='cuda')
 
     def run(k):
         times = []
         for i in range(k):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            pipe.unet(lat, 500.0, emb)
+            pipe.unet(lat, t_dev, emb)
             b.record()
             times.append((a, b))
         torch.cuda.synchronize()
@@ -290,7 +291,7 @@ def leg_hook_overhead(args, spec, dtype, windows):
         def graphed():
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                pipe.unet(lat, 500.0, emb)
+                pipe.unet(lat, t_dev, emb)
             ts = []
             for _ in range(3):
                 g.replay()
