@@ -47,6 +47,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries (NCCL banners, cuDNN logs) may write to fd 1; the driver expects exactly one JSON line on stdout. Everything
+# this process prints to fd 1 is sent to stderr, and the JSON line alone goes to the real stdout at the end.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + '\n').encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # workload description
 # --------------------------------------------------------------------------------------------------------------------
@@ -420,7 +439,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(args):
@@ -445,6 +464,7 @@ def main():
     if args.dtype is None:
         args.dtype = 'bf16' if args.workload == 'sd21' else 'fp16'
     args.warmup = max(3, args.warmup)
+    capture_stdout()
 
     if args.impl == 'reference':
         run_reference(args)
@@ -511,7 +531,7 @@ def main():
         'cpu_baseline': cpu,
         'hook_overhead': overhead,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     D.close()
 
 
