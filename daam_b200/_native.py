@@ -20,7 +20,7 @@ ACC_NO_PDL = 0x100
 E_INVALID, E_UNSUPPORTED, E_CUDA = -1, -2, -3
 TOKENS = 77
 
-EXPORTS = ('daam_accumulate', 'daam_finalize', 'daam_word_heat_map', 'daam_expand_as', 'daam_abi_version',
+EXPORTS = ('daam_accumulate', 'daam_attention_probs', 'daam_accumulate_probs', 'daam_finalize', 'daam_finalize_per_key', 'daam_word_heat_map', 'daam_expand_as', 'daam_abi_version',
            'daam_last_error', 'daam_device_info', 'daam_launch_count')
 
 
@@ -66,8 +66,14 @@ def load() -> ctypes.CDLL:
     i32, u32, i64, vp, f32 = ctypes.c_int32, ctypes.c_uint32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float
     lib.daam_accumulate.argtypes = [ctypes.POINTER(DaamLayer), i32, u32, vp]
     lib.daam_accumulate.restype = ctypes.c_int
+    lib.daam_attention_probs.argtypes = [ctypes.POINTER(DaamLayer), vp, vp]
+    lib.daam_attention_probs.restype = ctypes.c_int
+    lib.daam_accumulate_probs.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.daam_accumulate_probs.restype = ctypes.c_int
     lib.daam_finalize.argtypes = [ctypes.POINTER(DaamKeyGroup), i32, i32, i32, i32, vp, vp]
     lib.daam_finalize.restype = ctypes.c_int
+    lib.daam_finalize_per_key.argtypes = [ctypes.POINTER(DaamKeyGroup), i32, i32, i32, i32, vp, vp]
+    lib.daam_finalize_per_key.restype = ctypes.c_int
     lib.daam_word_heat_map.argtypes = [vp, i32, i32, ctypes.POINTER(i32), i32, vp, vp]
     lib.daam_word_heat_map.restype = ctypes.c_int
     lib.daam_expand_as.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp]
@@ -107,11 +113,27 @@ def accumulate(layers, stream: int, flags: int = ACC_AUTO):
         _check(rc)
 
 
+def attention_probs(layer: DaamLayer, probs_ptr: int, stream: int):
+    _check(load().daam_attention_probs(ctypes.byref(layer), probs_ptr, stream))
+
+
+def accumulate_probs(probs_ptr: int, dtype: int, first_row: int, n_rows: int, hw: int, tokens: int, acc_ptr: int,
+                     stream: int):
+    _check(load().daam_accumulate_probs(probs_ptr, dtype, first_row, n_rows, hw, tokens, acc_ptr, stream))
+
+
 def finalize(groups: Sequence[DaamKeyGroup], x: int, n_rows: int, normalize: bool, out_ptr: int, stream: int):
     n = len(groups)
     arr = (DaamKeyGroup * max(n, 1))(*groups)
     _check(load().daam_finalize(arr, n, x, n_rows, int(bool(normalize)), ctypes.c_void_p(out_ptr),
                                 ctypes.c_void_p(stream)))
+
+
+def finalize_per_key(groups: Sequence[DaamKeyGroup], x: int, n_rows: int, normalize: bool, out_ptr: int, stream: int):
+    n = len(groups)
+    arr = (DaamKeyGroup * max(n, 1))(*groups)
+    _check(load().daam_finalize_per_key(arr, n, x, n_rows, int(bool(normalize)), ctypes.c_void_p(out_ptr),
+                                        ctypes.c_void_p(stream)))
 
 
 def word_heat_map(maps_ptr: int, n_rows: int, x: int, rows: Sequence[int], out_ptr: int, stream: int):

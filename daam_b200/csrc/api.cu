@@ -49,14 +49,15 @@ int get_device_info(DeviceInfo* out) {
 static size_t dtype_size(int dtype) { return dtype == DAAM_F32 ? 4 : 2; }
 
 // Validates one layer call and fills the device-side descriptor (tile_begin is set by the packer).
-static int make_layer_params(const daam_layer& in, int index, LayerParams* out) {
-  if (!in.q || !in.k || !in.acc) { set_error("daam_accumulate: layer %d has a null pointer", index); return DAAM_E_INVALID; }
+int make_layer_params(const daam_layer& in, int index, LayerParams* out, bool need_acc);
+int make_layer_params(const daam_layer& in, int index, LayerParams* out, bool need_acc) {
+  if (!in.q || !in.k || (need_acc && !in.acc)) { set_error("daam_accumulate: layer %d has a null pointer", index); return DAAM_E_INVALID; }
   if (in.dtype != DAAM_F32 && in.dtype != DAAM_F16 && in.dtype != DAAM_BF16) { set_error("daam_accumulate: layer %d: unknown dtype %d", index, in.dtype); return DAAM_E_INVALID; }
   if (in.tokens != kTokens) { set_error("daam_accumulate: layer %d: tokens = %d, only %d is traced (daam/trace.py:289)", index, in.tokens, kTokens); return DAAM_E_UNSUPPORTED; }
   if (in.head_dim <= 0 || in.head_dim % 8 != 0 || in.head_dim > DAAM_MAX_HEAD_DIM) { set_error("daam_accumulate: layer %d: head_dim = %d must be a multiple of 8 in (0, %d]", index, in.head_dim, DAAM_MAX_HEAD_DIM); return DAAM_E_UNSUPPORTED; }
   if (in.n_prompts <= 0 || in.heads <= 0 || in.hw <= 0) { set_error("daam_accumulate: layer %d: non-positive n_prompts/heads/hw", index); return DAAM_E_INVALID; }
   if (in.hw % 4 != 0) { set_error("daam_accumulate: layer %d: hw = %d must be a multiple of 4", index, in.hw); return DAAM_E_UNSUPPORTED; }
-  if (reinterpret_cast<uintptr_t>(in.acc) % 16 != 0) { set_error("daam_accumulate: layer %d: acc is not 16-byte aligned", index); return DAAM_E_INVALID; }
+  if (need_acc && reinterpret_cast<uintptr_t>(in.acc) % 16 != 0) { set_error("daam_accumulate: layer %d: acc is not 16-byte aligned", index); return DAAM_E_INVALID; }
   if (!(in.scale > 0.f)) { set_error("daam_accumulate: layer %d: scale must be positive", index); return DAAM_E_INVALID; }
   LayerParams& L = *out;
   L.q = in.q; L.k = in.k; L.acc = in.acc;
@@ -104,7 +105,7 @@ extern "C" int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint3
   };
   for (int i = 0; i < n_layers; ++i) {
     LayerParams L;
-    if (int rc = make_layer_params(layers[i], i, &L)) return rc;
+    if (int rc = make_layer_params(layers[i], i, &L, /*need_acc=*/true)) return rc;
     bool use_mma = path != DAAM_ACC_FORCE_SIMT && mma_supported(L);
     if (path == DAAM_ACC_FORCE_MMA && !use_mma) {
       set_error("daam_accumulate: layer %d cannot take the tcgen05 path (dtype %d, head_dim %d, alignment %d)", i,

@@ -93,10 +93,40 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
   out[(long long)t * x * x + o] = sum / (float)P.n_keys;
 }
 
+// One output map per selected key (no mean): out[key][row][x][x] = clamp(bicubic(key[row])). grid: (ceil(x*x/256), n_rows,
+// n_keys); key k belongs to group g with first_key[g] <= k < first_key[g + 1].
+struct PerKeyParams {
+  int n_groups, x, n_rows, n_keys;
+  int first_key[kMaxGroups + 1];
+  daam_key_group g[kMaxGroups];
+};
+
+__global__ void __launch_bounds__(256) finalize_per_key_kernel(const __grid_constant__ PerKeyParams P, float* __restrict__ out) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y, key = blockIdx.z;
+  const int x = P.x;
+  if (o >= x * x) return;
+  int g = 0;
+  while (g + 1 < P.n_groups && key >= P.first_key[g + 1]) ++g;
+  const daam_key_group& G = P.g[g];
+  const int head = (G.head_sel < 0 ? 0 : G.head_sel) + (key - P.first_key[g]);
+  const int hw = G.h * G.w;
+  const float* src = G.acc + ((long long)head * G.tokens + t) * hw;
+  float v;
+  if (G.h == x && G.w == x) {
+    v = __ldg(src + o);
+  } else {
+    const int oy = o / x, ox = o - oy * x;
+    v = bicubic_at(src, G.w, make_taps(oy, G.h, x), make_taps(ox, G.w, x));
+  }
+  out[((long long)key * P.n_rows + t) * x * x + o] = fmaxf(v, 0.f);
+}
+
 // maps / (maps[1:-1].sum(0) + 1e-6), in place (daam/trace.py:129-130)
 __global__ void normalize_kernel(float* __restrict__ maps, int n_rows, int xx) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= xx) return;
+  maps += (long long)blockIdx.y * n_rows * xx;      // blockIdx.y: independent map stacks (per-key finalize)
   float s = 0.f;
   for (int t = 1; t < n_rows - 1; ++t) s += maps[(long long)t * xx + o];
   s += 1e-6f;
@@ -196,6 +226,41 @@ extern "C" int daam_finalize(const daam_key_group* groups, int32_t n_groups, int
   count_launch();
   if (normalize) {
     normalize_kernel<<<(xx + 255) / 256, 256, 0, stream>>>(out, n_rows, xx);
+    DAAM_CUDA_TRY(cudaGetLastError());
+    count_launch();
+  }
+  return DAAM_OK;
+}
+
+extern "C" int daam_finalize_per_key(const daam_key_group* groups, int32_t n_groups, int32_t x, int32_t n_rows,
+                                     int32_t normalize, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!groups || !out || x <= 0 || n_rows <= 0) { set_error("daam_finalize_per_key: null pointer or non-positive size"); return DAAM_E_INVALID; }
+  if (n_groups <= 0) { set_error("daam_finalize_per_key: no key selected"); return DAAM_E_INVALID; }
+  if (n_groups > kMaxGroups) { set_error("daam_finalize_per_key: %d key groups > %d", n_groups, kMaxGroups); return DAAM_E_UNSUPPORTED; }
+  DeviceInfo dev;
+  if (int rc = get_device_info(&dev)) return rc;
+  static thread_local PerKeyParams p;
+  p.n_groups = n_groups; p.x = x; p.n_rows = n_rows; p.n_keys = 0;
+  for (int i = 0; i < n_groups; ++i) {
+    const daam_key_group& g = groups[i];
+    if (!g.acc || g.heads <= 0 || g.h <= 0 || g.w <= 0 || g.tokens < n_rows || g.head_sel >= g.heads) {
+      set_error("daam_finalize_per_key: bad key group %d", i);
+      return DAAM_E_INVALID;
+    }
+    p.g[i] = g;
+    p.first_key[i] = p.n_keys;
+    p.n_keys += g.head_sel < 0 ? g.heads : 1;
+  }
+  p.first_key[n_groups] = p.n_keys;
+  if (p.n_keys > 65535) { set_error("daam_finalize_per_key: %d keys > 65535", p.n_keys); return DAAM_E_UNSUPPORTED; }
+  const int xx = x * x;
+  dim3 grid((xx + 255) / 256, n_rows, p.n_keys);
+  finalize_per_key_kernel<<<grid, 256, 0, stream>>>(p, out);
+  DAAM_CUDA_TRY(cudaGetLastError());
+  count_launch();
+  if (normalize) {   // every key's map is an independent [n_rows, x, x] block
+    normalize_kernel<<<dim3((xx + 255) / 256, p.n_keys), 256, 0, stream>>>(out, n_rows, xx);
     DAAM_CUDA_TRY(cudaGetLastError());
     count_launch();
   }

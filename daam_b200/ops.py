@@ -12,7 +12,8 @@ import torch
 
 from . import _native
 
-__all__ = ['cond_half', 'make_layer_desc', 'new_accumulator', 'pack', 'accumulate', 'accumulate_layer']
+__all__ = ['cond_half', 'make_layer_desc', 'new_accumulator', 'pack', 'accumulate', 'accumulate_layer',
+           'attention_probs', 'accumulate_probs']
 
 _DTYPES = {torch.float32: _native.DAAM_F32, torch.float16: _native.DAAM_F16, torch.bfloat16: _native.DAAM_BF16}
 
@@ -92,3 +93,46 @@ def accumulate_layer(q: torch.Tensor, k: torch.Tensor, heads: int, scale: Option
         scale = (chan // heads) ** -0.5
     accumulate([make_layer_desc(q, k, acc, heads, scale)], q.device, flags=flags)
     return acc
+
+
+def attention_probs(q: torch.Tensor, k: torch.Tensor, heads: int, scale: Optional[float] = None) -> torch.Tensor:
+    """Materialised ``softmax(scale * Q K^T)`` for EVERY sample: ``[B*heads, hw, 77]`` in the dtype of ``q`` -- what
+    diffusers' ``get_attention_scores`` returns at daam/trace.py:276 (rows ordered ``b*heads + head``). Compatibility
+    path for ``save_heads``; the traced hot path never materialises this tensor."""
+    if not (q.is_cuda and k.is_cuda):
+        raise RuntimeError('daam_b200 computes on CUDA tensors only (there is no CPU fallback)')
+    if q.dtype not in _DTYPES or k.dtype != q.dtype:
+        raise RuntimeError(f'unsupported projection dtypes {q.dtype}/{k.dtype}')
+    if q.stride(-1) != 1 or k.stride(-1) != 1:
+        q, k = q.contiguous(), k.contiguous()
+    bsz, hw, chan = q.shape
+    d = chan // heads
+    if scale is None:
+        scale = d ** -0.5
+    probs = torch.empty((bsz * heads, hw, k.shape[1]), dtype=q.dtype, device=q.device)
+    desc = _native.DaamLayer(
+        q=q.data_ptr(), k=k.data_ptr(), acc=None,
+        q_stride_prompt=q.stride(0), q_stride_pixel=q.stride(1), q_stride_head=d,
+        k_stride_prompt=k.stride(0), k_stride_token=k.stride(1), k_stride_head=d,
+        n_prompts=bsz, heads=heads, hw=hw, tokens=k.shape[1], head_dim=d,
+        dtype=_DTYPES[q.dtype], scale=float(scale), reserved=0)
+    with torch.cuda.device(q.device):
+        _native.attention_probs(desc, probs.data_ptr(), torch.cuda.current_stream(q.device).cuda_stream)
+    return probs
+
+
+def accumulate_probs(probs: torch.Tensor, acc: torch.Tensor):
+    """``acc[r][t][pixel] += probs[first + r][pixel][t]`` with ``first = rows // 2``: the reference's "second half of
+    the batch*heads axis" (daam/trace.py:240) applied to supplied probabilities (``load_heads``, trace.py:281-294).
+    ``acc``: fp32 ``[n_prompts, n_heads, 77, hw]`` (its leading two axes flatten to the kept rows)."""
+    if not (probs.is_cuda and acc.is_cuda):
+        raise RuntimeError('daam_b200 computes on CUDA tensors only (there is no CPU fallback)')
+    probs = probs.contiguous()
+    rows, hw, tokens = probs.shape
+    first = rows // 2
+    kept = rows - first
+    if acc.dtype != torch.float32 or not acc.is_contiguous() or acc.numel() != kept * tokens * hw:
+        raise RuntimeError(f'accumulator must be contiguous fp32 with {kept} x {tokens} x {hw} elements')
+    with torch.cuda.device(probs.device):
+        _native.accumulate_probs(probs.data_ptr(), _DTYPES[probs.dtype], first, kept, hw, tokens, acc.data_ptr(),
+                                 torch.cuda.current_stream(probs.device).cuda_stream)

@@ -48,10 +48,6 @@ class DiffusionHeatMapHooker(AggregateHooker):
                  locate_middle_block: bool = False, kernel_flags: int = _native.ACC_AUTO):
         if launch not in ('step', 'layer'):
             raise ValueError("launch must be 'step' or 'layer'")
-        if load_heads or save_heads:
-            raise NotImplementedError(
-                'save_heads/load_heads need the materialised probabilities (reference trace.py:246-250, 279-282); '
-                'that compatibility path is listed as "next" in SURVEY.md section 8f and is not built yet')
         _native.load()   # fail here, loudly, if the CUDA library is missing
         self.all_heat_maps = RawHeatMapCollection()
         side = pipeline.unet.config.sample_size * pipeline.vae_scale_factor
@@ -74,7 +70,8 @@ class DiffusionHeatMapHooker(AggregateHooker):
         self.all_heat_maps.bind(self.synchronize, self._zero_slabs)
 
         modules = [
-            UNetCrossAttentionHooker(m, self, layer_idx=idx, latent_hw=self.latent_hw, data_dir=data_dir)
+            UNetCrossAttentionHooker(m, self, layer_idx=idx, latent_hw=self.latent_hw, load_heads=load_heads,
+                                     save_heads=save_heads, data_dir=data_dir)
             for idx, m in enumerate(self.locator.locate(pipeline.unet))
         ]
         modules.append(PipelineHooker(pipeline, self))
@@ -92,8 +89,14 @@ class DiffusionHeatMapHooker(AggregateHooker):
         return self.locator.layer_names
 
     def to_experiment(self, path, seed=None, id='.', subtype='.', **compute_kwargs):
-        raise NotImplementedError('GenerationExperiment persistence (reference daam/experiment.py) is outside the '
-                                  'hot-path scope; use compute_global_heat_map().heat_maps')
+        """Exports the last generation call to a serializable generation experiment (trace.py:68-81)."""
+        from .experiment import GenerationExperiment
+        return GenerationExperiment(
+            self.last_image,
+            self.compute_global_heat_map(**compute_kwargs).heat_maps,
+            self.last_prompt,
+            seed=seed, id=id, subtype=subtype, path=path, tokenizer=self.pipe.tokenizer,
+        )
 
     def _hook_impl(self):
         super()._hook_impl()
@@ -152,6 +155,17 @@ class DiffusionHeatMapHooker(AggregateHooker):
             return
         self._pending.append((layer_idx, desc, q, k, slab.acc))   # tensors kept alive until the launch
         self._pending_layers.add(layer_idx)
+
+    def _accumulate_probs(self, layer_idx: int, factor: int, probs: torch.Tensor, bsz: int, heads: int):
+        """Heat maps from materialised probabilities (save_heads / load_heads compatibility path)."""
+        hw = probs.shape[1]
+        side = int(math.sqrt(hw))
+        _, n_prompts, head0, n_heads = ops.cond_half(bsz, heads)
+        if n_prompts > 1 and not self.batch_prompts:
+            raise ValueError('Only single prompt generation is supported for heat map computation.')
+        slab = self.all_heat_maps.slab_for(layer_idx, factor, n_prompts, n_heads, side, side, probs.device, head0)
+        self.synchronize()
+        ops.accumulate_probs(probs, slab.acc)
 
     def flush(self):
         """Issue the queued layer calls as one persistent launch on the side stream."""
@@ -227,6 +241,35 @@ class DiffusionHeatMapHooker(AggregateHooker):
         return GlobalHeatMap(self.pipe.tokenizer, prompt, maps)
 
 
+    def compute_per_head_heat_maps(self, prompt=None, factors=None, normalize=False, prompt_idx: int = 0):
+        """Every ``compute_global_heat_map(layer_idx=l, head_idx=h)`` of the reference's ``--all-heads`` sweep
+        (daam/run/generate.py:239-255) in one launch. Returns ``(keys, maps)``: ``keys[i] = (factor, layer, head)`` and
+        ``maps[i]`` the ``[n_tokens + 2, x, x]`` heat map the reference computes for that single key."""
+        if prompt is None:
+            prompt = self.last_prompts[prompt_idx] if self.last_prompts else self.last_prompt
+        factors = {0, 1, 2, 4, 8, 16, 32, 64} if factors is None else set(factors)
+        x = int(np.sqrt(self.latent_hw))
+        self.synchronize()
+        groups, keep, keys = [], [], []
+        for slab in self.all_heat_maps.live_slabs():
+            if slab.factor not in factors:
+                continue
+            acc = slab.acc[prompt_idx]
+            groups.append(_native.DaamKeyGroup(acc=acc.data_ptr(), heads=slab.heads, h=slab.h, w=slab.w,
+                                               tokens=acc.shape[1], head_sel=-1, reserved=0))
+            keep.append(acc)
+            keys += [(slab.factor, slab.layer_idx, head) for head in range(slab.heads)]
+        if not groups:
+            raise RuntimeError('No heat maps found. Did you forget to call `with trace(...)` during generation?')
+        n_rows = min(len(self.pipe.tokenizer.tokenize(prompt)) + 2, _native.TOKENS)
+        device = keep[0].device
+        maps = torch.empty((len(keys), n_rows, x, x), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            _native.finalize_per_key(groups, x, n_rows, normalize, maps.data_ptr(),
+                                     torch.cuda.current_stream(device).cuda_stream)
+        return keys, maps
+
+
 class ImageProcessorHooker(ObjectHooker):
     """Remembers the first post-processed image of an SDXL pipeline (trace.py:135-147)."""
 
@@ -295,6 +338,34 @@ class UNetCrossAttentionHooker(ObjectHooker):
         self.save_heads = save_heads
         self.trace = parent_trace
         self.data_dir = Path(data_dir) if data_dir is not None else cache_dir() / 'heads'
+        if load_heads or save_heads:
+            self.data_dir.mkdir(parents=True, exist_ok=True)
+
+    def _save_attn(self, attn_slice: torch.Tensor):
+        torch.save(attn_slice, self.data_dir / f'{self.trace._gen_idx}.pt')
+
+    def _load_attn(self) -> torch.Tensor:
+        return torch.load(self.data_dir / f'{self.trace._gen_idx}.pt')
+
+    def _materialised_call(self, attn, query, key, value):
+        """save_heads / load_heads (trace.py:276-302): the probabilities exist as a tensor -- written to / replaced
+        from ``data_dir/{gen_idx}.pt`` -- heat maps and the layer output are both computed from that tensor."""
+        bsz, n, _ = query.shape
+        heads, tokens = attn.heads, key.shape[1]
+        if self.save_heads:
+            probs = ops.attention_probs(query, key, heads, attn.scale)     # [B*H, hw, 77], dtype of the pipeline
+            self._save_attn(probs)
+        else:
+            probs = self._load_attn().to(query.device)
+        factor = int(math.sqrt(self.latent_hw // probs.shape[1]))
+        self.trace._gen_idx += 1
+        if probs.shape[-1] == self.context_size and factor != 8:
+            self.trace._accumulate_probs(self.layer_idx, factor, probs, bsz, heads)
+        d = value.shape[-1] // heads
+        v = value.view(bsz, tokens, heads, d).permute(0, 2, 1, 3).reshape(bsz * heads, tokens, d)
+        out = torch.bmm(probs.to(v.dtype), v)
+        out = out.view(bsz, heads, n, d).permute(0, 2, 1, 3).reshape(bsz, n, heads * d)
+        return attn.to_out[1](attn.to_out[0](out))
 
     @torch.no_grad()
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None):
@@ -309,6 +380,9 @@ class UNetCrossAttentionHooker(ObjectHooker):
             encoder_hidden_states = attn.norm_cross(encoder_hidden_states)
         key = attn.to_k(encoder_hidden_states)
         value = attn.to_v(encoder_hidden_states)
+
+        if self.save_heads or self.load_heads:
+            return self._materialised_call(attn, query, key, value)
 
         heads = attn.heads
         tokens = key.shape[1]

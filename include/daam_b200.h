@@ -81,6 +81,24 @@ typedef struct daam_layer {
 int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint32_t flags, void* stream);
 
 /*
+ * Compatibility path of the reference's save_heads: materialise what Attention.get_attention_scores returns
+ * (daam/trace.py:276) so that it can be saved like daam/trace.py:246-247, 279-280 do:
+ *   probs[(p*heads + head)][pixel][t] = softmax_t(scale * <q, k>)   for every sample p in [0, n_prompts)
+ * in the dtype of q (device, contiguous [n_prompts*heads][hw][77]). `layer` describes the WHOLE batch here (q/k point
+ * at sample 0, n_prompts = batch size); layer->acc is ignored. Runs the SIMT fp32 kernel for every dtype.
+ */
+int daam_attention_probs(const daam_layer* layer, void* probs, void* stream);
+
+/*
+ * Compatibility path of the reference's load_heads (daam/trace.py:281-294): heat maps from supplied probabilities,
+ *   acc[r][t][pixel] += probs[first_row + r][pixel][t]     for r in [0, n_rows)
+ * i.e. _unravel_attn + the update loop with rows = kept (sample, head) pairs; probs is [*][hw][77] of `dtype`,
+ * acc fp32 [n_rows][77][hw].
+ */
+int daam_accumulate_probs(const void* probs, int32_t dtype, int32_t first_row, int32_t n_rows, int32_t hw,
+                          int32_t tokens, float* acc, void* stream);
+
+/*
  * All (or one) heads of one traced layer: `acc` points at [heads][tokens][h*w] fp32 (one prompt's slice of the
  * accumulator daam_accumulate fills). head_sel = -1 selects every head, otherwise one head index.
  */
@@ -100,6 +118,15 @@ typedef struct daam_key_group {
  */
 int daam_finalize(const daam_key_group* groups, int32_t n_groups, int32_t x, int32_t n_rows, int32_t normalize,
                   float* out, void* stream);
+
+/*
+ * The reference's --all-heads sweep calls compute_global_heat_map(layer_idx=l, head_idx=h) once per (layer, head)
+ * (daam/run/generate.py:239-255): each call reduces exactly one key, i.e. bicubic + clamp (+ normalise) of that key.
+ * This entry point produces all of them in one launch: out [n_keys][n_rows][x][x] (device fp32), keys enumerated
+ * group by group, head by head, in the order given.
+ */
+int daam_finalize_per_key(const daam_key_group* groups, int32_t n_groups, int32_t x, int32_t n_rows, int32_t normalize,
+                          float* out, void* stream);
 
 /*
  * Replaces GlobalHeatMap.compute_word_heat_map's tensor part (daam/heatmap.py:121-123): mean over the rows

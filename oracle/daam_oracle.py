@@ -166,6 +166,9 @@ class OracleProcessor:
         self.module, self.parent, self.layer_idx = module, parent, layer_idx
         self.saved = None
 
+    def _path(self):
+        return self.parent.data_dir / f'{self.parent.gen_idx}.pt'     # daam/trace.py:246-250
+
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None):
         bsz, n, _ = hidden_states.shape
         attention_mask = attn.prepare_attention_mask(attention_mask, n, bsz)
@@ -176,6 +179,10 @@ class OracleProcessor:
         k, v = attn.to_k(ctx), attn.to_v(ctx)
         q, k, v = attn.head_to_batch_dim(q), attn.head_to_batch_dim(k), attn.head_to_batch_dim(v)
         probs = port_attention_probs(attn, q, k, attention_mask)
+        if self.parent.save_heads:                                    # daam/trace.py:279-282
+            torch.save(probs, self._path())
+        elif self.parent.load_heads:
+            probs = torch.load(self._path())
         factor = port_factor(self.parent.latent_hw, probs.shape[1])
         self.parent.gen_idx += 1
         if port_traced(probs.shape[-1], factor):
@@ -189,8 +196,13 @@ class OracleTrace:
     """The reference's ``trace`` context manager reduced to the hot path (daam/trace.py:22-132, 150-186): hooks every
     located attn2, clears the store at ``check_inputs``, exposes ``compute_global_heat_map``."""
 
-    def __init__(self, pipe, low_memory: bool = False, locate_middle_block: bool = False):
+    def __init__(self, pipe, low_memory: bool = False, locate_middle_block: bool = False, save_heads: bool = False,
+                 load_heads: bool = False, data_dir=None):
+        from pathlib import Path
         self.pipe = pipe
+        self.save_heads, self.load_heads = save_heads, load_heads
+        self.data_dir = Path(data_dir) if data_dir is not None else None
+        locate_middle_block = locate_middle_block or save_heads or load_heads     # daam/trace.py:34-35
         self.heat_maps = OracleHeatMaps()
         self.latent_hw = port_latent_hw(pipe.unet.config.sample_size, pipe.vae_scale_factor)
         self.layers, self.layer_names = port_locate(pipe.unet, {0} if low_memory else None, locate_middle_block)

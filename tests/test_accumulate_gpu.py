@@ -256,3 +256,27 @@ def test_full_size_sd21_step_properties():
     for i in (0, 3, 6):
         hw, h = shapes[i]
         assert_close(one[i][0], oracle_layer_maps(qs[i], ks[i], h, 0.125), TOL[torch.bfloat16], f'layer {i}')
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-5), (torch.float16, 1e-3), (torch.bfloat16, 8e-3)])
+@pytest.mark.parametrize('hw,heads,d', [(1024, 4, 64), (576, 2, 64), (64, 2, 40), (4096, 1, 64)])
+def test_materialised_probs_match_get_attention_scores(hw, heads, d, dtype, tol):
+    """daam_attention_probs == diffusers' get_attention_scores (reference call at trace.py:276) for every sample;
+    daam_accumulate_probs == _unravel_attn + update on that tensor. Tolerance: one rounding to the output dtype."""
+    from daam_b200.synthetic import SyntheticAttention
+    g = torch.Generator().manual_seed(hw + d)
+    q = torch.randn(2, hw, heads * d, generator=g).to(dtype).to(DEV)
+    k = torch.randn(2, 77, heads * d, generator=g).to(dtype).to(DEV)
+    probs = ops.attention_probs(q, k, heads)
+    torch.cuda.synchronize()
+    assert probs.shape == (2 * heads, hw, 77) and probs.dtype == dtype
+    attn = SyntheticAttention(heads * d, heads * d, heads, d)
+    ref = attn.get_attention_scores(attn.head_to_batch_dim(q.float().cpu()), attn.head_to_batch_dim(k.float().cpu()))
+    assert rel_err(probs.float(), ref) < tol
+    acc = ops.new_accumulator(1, heads, hw, DEV)
+    ops.accumulate_probs(probs, acc)
+    ops.accumulate_probs(probs, acc)
+    torch.cuda.synchronize()
+    from oracle import daam_oracle as O
+    want = 2 * O.port_unravel(probs.float().cpu()).reshape(heads, 77, hw)
+    assert rel_err(acc[0], want) < 1e-6

@@ -143,9 +143,44 @@ def test_latent_hw_rule():
         assert trace(pipe).latent_hw == expect
 
 
-def test_unsupported_compat_options_are_explicit():
+def test_bad_options_are_rejected():
     pipe = make_pipeline(TINY_SPEC)
-    with pytest.raises(NotImplementedError):
-        trace(pipe, save_heads=True)
     with pytest.raises(ValueError):
         trace(pipe, launch='sometimes')
+
+
+def test_generation_experiment_roundtrip_and_reference_dump(tmp_path):
+    """Same folder layout as the reference (experiment.py:140-175); dumps pickled under the reference's class path load."""
+    import pickle
+    import sys
+    import types
+    from daam_b200 import GenerationExperiment
+    tok = WhitespaceTokenizer()
+    maps = torch.rand(5, 8, 8)
+    exp = GenerationExperiment(image=None, global_heat_map=maps, prompt='a red ball', seed=7, id='p0', path=str(tmp_path),
+                               tokenizer=tok).annotate('k', 1)
+    exp.save()
+    assert (tmp_path / 'p0' / 'generation.pt').exists() and (tmp_path / 'p0' / 'prompt.txt').read_text() == 'a red ball'
+    assert GenerationExperiment.read_seed(tmp_path, 'p0') == 7 and GenerationExperiment.has_experiment(tmp_path, 'p0')
+    back = GenerationExperiment.load(tmp_path / 'p0')
+    assert back.prompt == 'a red ball' and torch.equal(back.global_heat_map, maps) and back.annotations == {'k': 1}
+    assert back.heat_map().prompt == 'a red ball'
+    # a dump written by the reference pickles the class as daam.experiment.GenerationExperiment
+    fake = types.ModuleType('daam.experiment')
+    fake.GenerationExperiment = type('GenerationExperiment', (), {'__module__': 'daam.experiment'})
+    sys.modules.setdefault('daam', types.ModuleType('daam'))
+    had = sys.modules.get('daam.experiment')
+    sys.modules['daam.experiment'] = fake
+    try:
+        obj = fake.GenerationExperiment()
+        obj.__dict__.update(image=None, global_heat_map=maps, prompt='ref prompt', seed=1, id='.', path=None,
+                            truth_masks=None, prediction_masks=None, annotations=None, subtype='.', tokenizer=None)
+        (tmp_path / 'ref').mkdir()
+        torch.save(obj, tmp_path / 'ref' / 'generation.pt')
+    finally:
+        if had is None:
+            del sys.modules['daam.experiment']
+        else:
+            sys.modules['daam.experiment'] = had
+    ref = GenerationExperiment.load(tmp_path / 'ref')
+    assert isinstance(ref, GenerationExperiment) and ref.prompt == 'ref prompt' and torch.equal(ref.global_heat_map, maps)

@@ -112,3 +112,51 @@ def test_math_layer_agrees_with_port(runs):
     np.testing.assert_allclose(ref_out['global'].numpy(), g, rtol=2e-5, atol=2e-6)
     gn = O.math_global_heat_map(keys, 64, n_rows, normalize=True)
     np.testing.assert_allclose(ref_out['norm'].numpy(), gn, rtol=2e-5, atol=2e-6)
+
+
+def test_save_and_load_heads_match_reference(ref, tmp_path):
+    """save_heads writes the same `{gen_idx}.pt` tensors; load_heads replays them into the same maps (trace.py:246-282)."""
+    pipe = make_pipeline(TINY_SPEC, dtype=torch.float32, seed=5)
+    d_ref, d_ora = tmp_path / 'ref', tmp_path / 'ora'
+    gen = lambda: torch.Generator().manual_seed(2)
+    with ref.trace(pipe, save_heads=True, data_dir=str(d_ref)) as tc:
+        pipe(PROMPT, num_inference_steps=2, generator=gen())
+        saved_ref = tc.compute_global_heat_map().heat_maps.clone()
+        assert len(tc.layer_names) == 16          # save/load also locate the mid block
+    d_ora.mkdir()
+    with O.OracleTrace(pipe, save_heads=True, data_dir=d_ora) as ot:
+        pipe(PROMPT, num_inference_steps=2, generator=gen())
+        saved_ora = ot.compute_global_heat_map()
+    names = sorted(p.name for p in d_ref.iterdir())
+    assert names == sorted(p.name for p in d_ora.iterdir()) and len(names) == 32
+    for nme in names:
+        assert torch.equal(torch.load(d_ref / nme), torch.load(d_ora / nme)), nme
+    assert torch.equal(saved_ref, saved_ora)
+    other = make_pipeline(TINY_SPEC, dtype=torch.float32, seed=6)     # different weights: P comes from the files
+    with ref.trace(other, load_heads=True, data_dir=str(d_ref)) as tc:
+        out_ref = other(PROMPT, num_inference_steps=2, generator=gen()).latents
+        loaded_ref = tc.compute_global_heat_map().heat_maps.clone()
+    with O.OracleTrace(other, load_heads=True, data_dir=d_ref) as ot:
+        out_ora = other(PROMPT, num_inference_steps=2, generator=gen()).latents
+        loaded_ora = ot.compute_global_heat_map()
+    assert torch.equal(loaded_ref, loaded_ora) and torch.equal(out_ref, out_ora)
+    assert torch.equal(loaded_ref, saved_ref)     # the maps depend on the loaded probabilities only
+
+
+def test_reference_experiment_dump_loads_in_daam_b200(ref, tmp_path):
+    """generation.pt written by the reference's GenerationExperiment.save (experiment.py:140-167) loads in ours, and back."""
+    import PIL.Image
+    from daam_b200 import GenerationExperiment
+    maps = torch.rand(6, 16, 16)
+    img = PIL.Image.new('RGB', (16, 16), (10, 20, 30))
+    exp = ref.GenerationExperiment(img, maps, 'a red ball', seed=3, id='q1', path=str(tmp_path))
+    exp.save(heat_maps=False)
+    ours = GenerationExperiment.load(tmp_path / 'q1')
+    assert ours.prompt == 'a red ball' and ours.seed == 3 and torch.equal(ours.global_heat_map, maps)
+    assert ours.image.size == (16, 16)
+    ours.id = '.'
+    ours.save(str(tmp_path / 'again'))
+    # same folder layout both ways (the reference's own `load` calls torch.load without weights_only=False and therefore
+    # cannot read ANY pickled experiment under torch >= 2.6, its own included, so the reverse direction is checked by name)
+    listing = lambda root: sorted(str(p.relative_to(root)) for p in root.rglob('*') if p.is_file())
+    assert listing(tmp_path / 'again') == listing(tmp_path / 'q1')

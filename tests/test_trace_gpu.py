@@ -175,3 +175,68 @@ def test_cuda_graph_replay_traces_like_eager(launch):
         assert any(st['graph'] is not None for st in graph_pipe._graphs.values())
     base = graph_pipe(prompt, num_inference_steps=3)     # un-hooked: new processors -> new graph, still runs
     assert base.latents.shape[0] == 1
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.float16, 2e-3)])
+def test_save_heads_and_load_heads(tmp_path, dtype, tol):
+    """Compatibility path (reference trace.py:246-250, 279-302): probabilities are materialised per layer call as
+    `{gen_idx}.pt` ([B*H, hw, 77], pipeline dtype); load_heads recomputes maps and layer outputs from those files."""
+    steps = 2
+    pipe = make_pipeline(TINY_SPEC, dtype=dtype, device=DEV, seed=5)
+    with trace(pipe, save_heads=True, data_dir=str(tmp_path)) as tc:
+        assert len(tc.layer_names) == 16
+        out_save = pipe(PROMPT, num_inference_steps=steps, generator=torch.Generator().manual_seed(2)).latents
+        maps_save = tc.compute_global_heat_map().heat_maps.clone()
+        keys_save = {k: v.clone() for k, v in tc.all_heat_maps}
+    files = sorted(tmp_path.iterdir(), key=lambda p: int(p.stem))
+    assert [int(p.stem) for p in files] == list(range(16 * steps))
+    # every saved tensor is a row-stochastic [B*H, hw, 77] matrix in the pipeline dtype
+    shapes = set()
+    for p in files:
+        t = torch.load(p)
+        assert t.dtype == dtype and t.shape[-1] == 77
+        shapes.add(tuple(t.shape))
+        assert torch.allclose(t.float().sum(-1), torch.ones_like(t[..., 0]).float(), atol=5e-3)
+    assert (2 * 1, 4096, 77) in shapes and (2 * 2, 64, 77) in shapes          # 64x64 head and the mid block (8x8)
+    # the maps are exactly the time-sums of the conditional halves of the saved tensors (oracle: unravel + update)
+    store = O.OracleHeatMaps()
+    per_step = [torch.load(p).float().cpu() for p in files]
+    calls = list(range(9, 15)) + [15] + list(range(0, 9))     # execution order: down blocks, mid block, up blocks
+    for i, t in enumerate(per_step):
+        layer = calls[i % 16]
+        factor = int((4096 // t.shape[1]) ** 0.5)
+        if factor != 8:
+            for head, m in enumerate(O.port_unravel(t)):
+                store.update(factor, layer, head, m)
+    for key, ref in store:
+        assert rel_err(keys_save[key], ref) < 1e-5, key
+    # load_heads on a pipeline with other weights reproduces the maps from the files alone
+    other = make_pipeline(TINY_SPEC, dtype=dtype, device=DEV, seed=6)
+    with trace(other, load_heads=True, data_dir=str(tmp_path)) as tc:
+        other(PROMPT, num_inference_steps=steps, generator=torch.Generator().manual_seed(2))
+        maps_load = tc.compute_global_heat_map().heat_maps.clone()
+    assert torch.equal(maps_load, maps_save)
+    # and on the same pipeline it also reproduces the UNet output of the saving run
+    with trace(pipe, load_heads=True, data_dir=str(tmp_path)) as tc:
+        out_load = pipe(PROMPT, num_inference_steps=steps, generator=torch.Generator().manual_seed(2)).latents
+    assert rel_err(out_load, out_save) < 1e-6
+    # the materialised path and the fused path see the same attention: their maps agree
+    with trace(pipe) as tc:
+        pipe(PROMPT, num_inference_steps=steps, generator=torch.Generator().manual_seed(2))
+        fused = tc.compute_global_heat_map().heat_maps
+    assert rel_err(maps_save, fused) < tol
+
+
+def test_per_head_heat_maps_equal_the_all_heads_sweep():
+    """One launch == the reference's `for head, layer: compute_global_heat_map(layer_idx, head_idx)` loop."""
+    pipe = make_pipeline(TINY_SPEC, dtype=torch.float16, device=DEV, seed=8)
+    with trace(pipe) as tc:
+        pipe(PROMPT, num_inference_steps=2, generator=torch.Generator().manual_seed(1))
+        for normalize in (False, True):
+            keys, maps = tc.compute_per_head_heat_maps(normalize=normalize)
+            assert len(keys) == 25 and maps.shape == (25, 11, 64, 64)
+            for (factor, layer, head), m in zip(keys, maps):
+                single = tc.compute_global_heat_map(layer_idx=layer, head_idx=head, normalize=normalize).heat_maps
+                assert torch.equal(single, m), (factor, layer, head)
+        keys2, _ = tc.compute_per_head_heat_maps(factors=[2])
+        assert {k[0] for k in keys2} == {2}
