@@ -168,8 +168,9 @@ def test_generation_experiment_roundtrip_and_reference_dump(tmp_path):
     # a dump written by the reference pickles the class as daam.experiment.GenerationExperiment
     fake = types.ModuleType('daam.experiment')
     fake.GenerationExperiment = type('GenerationExperiment', (), {'__module__': 'daam.experiment'})
-    sys.modules.setdefault('daam', types.ModuleType('daam'))
-    had = sys.modules.get('daam.experiment')
+    had_pkg, had = sys.modules.get('daam'), sys.modules.get('daam.experiment')
+    if had_pkg is None:
+        sys.modules['daam'] = types.ModuleType('daam')
     sys.modules['daam.experiment'] = fake
     try:
         obj = fake.GenerationExperiment()
@@ -182,5 +183,7 @@ def test_generation_experiment_roundtrip_and_reference_dump(tmp_path):
             del sys.modules['daam.experiment']
         else:
             sys.modules['daam.experiment'] = had
+        if had_pkg is None:
+            del sys.modules['daam']
     ref = GenerationExperiment.load(tmp_path / 'ref')
     assert isinstance(ref, GenerationExperiment) and ref.prompt == 'ref prompt' and torch.equal(ref.global_heat_map, maps)
