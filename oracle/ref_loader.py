@@ -69,7 +69,7 @@ def load_reference():
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     stale = sys.modules.get('daam')
-    if stale is not None and not getattr(stale, '__file__', '').startswith(os.path.abspath(REFERENCE_ROOT)):
+    if stale is not None and not (getattr(stale, '__file__', None) or '').startswith(os.path.abspath(REFERENCE_ROOT)):
         for name in [n for n in sys.modules if n == 'daam' or n.startswith('daam.')]:
             del sys.modules[name]
     import daam  # noqa: E402  (the reference package)
