@@ -117,3 +117,29 @@ def test_word_heat_map_and_expand_golden():
     mism = (thr.numpy() != fx['expand_thr']).mean()
     assert mism < 1e-3      # binarisation may flip pixels that sit within rounding of the threshold
     assert w.compute_ioa(w) == pytest.approx(float((w.heatmap ** 2).sum() / w.heatmap.sum()), rel=1e-5)
+
+
+@pytest.mark.parametrize('x,sides', [(64, [64, 32, 16]), (96, [96, 48, 24]), (64, [16]), (32, [32, 8])])
+def test_fast_and_generic_finalize_agree(monkeypatch, x, sides):
+    """The phase-structured kernel for integer factors 1/2/4 vs the generic gather kernel (DAAM_FINALIZE_GENERIC=1),
+    on SD-like key sets (several heads per resolution, head filter, normalisation, partial 96-latent bands)."""
+    g = torch.Generator().manual_seed(x)
+    keep, groups = [], []
+    for i, side in enumerate(sides):
+        heads = 3 + i
+        t = torch.exp(2.0 * torch.randn(heads, 77, side, side, generator=g)).to(DEV)
+        keep.append(t)
+        groups.append(_native.DaamKeyGroup(acc=t.data_ptr(), heads=heads, h=side, w=side, tokens=77, head_sel=-1,
+                                           reserved=0))
+    for head_sel in (-1, 1):
+        for grp in groups:
+            grp.head_sel = head_sel
+        for normalize in (False, True):
+            monkeypatch.setenv('DAAM_FINALIZE_GENERIC', '0')
+            fast = run_finalize(groups, 23, normalize, x=x)
+            monkeypatch.setenv('DAAM_FINALIZE_GENERIC', '1')
+            slow = run_finalize(groups, 23, normalize, x=x)
+            assert rel_err(fast, slow) < 2e-6
+            keys = [k[h].cpu().numpy() for k in keep for h in (range(k.shape[0]) if head_sel < 0 else [head_sel])]
+            ref = O.math_global_heat_map(keys, x, 23, normalize)
+            assert rel_err(fast, ref) < 1e-5
