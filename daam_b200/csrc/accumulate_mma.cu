@@ -14,13 +14,11 @@
 //                           loads the accumulator;
 //                ldst mode: coalesced 128-byte load / add / store per warp and token, straight from registers.
 // Warp roles: 0-3 epilogue, 4 TMA producer (one elected thread), 5 TMEM allocator + MMA issuer (one thread).
-// Persistent: CTAs claim tiles one at a time from a launch-wide atomic counter (dynamic scheduling evens out the
-// two-die / first-load skew between CTAs); up to 2 CTAs per SM (256 TMEM columns each).
+// Persistent: every CTA walks a contiguous chunk of the launch's tiles; up to 2 CTAs per SM (256 TMEM columns each).
 //
 // Replaces daam/trace.py:276 (get_attention_scores), :219-244 (_unravel_attn) and :293-294 (update loop).
 #include <cuda.h>
 
-#include <atomic>
 #include <mutex>
 #include <unordered_map>
 #include <string>
@@ -39,11 +37,6 @@ constexpr int kTmemCols = 256;
 constexpr int kAccCols = 128;                         // column distance between the two accumulators
 constexpr int kThreads = 192;
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kPBytes + 128;
-
-// Dynamic tile scheduler: a ring of {next tile, finished CTAs} pairs, one pair per launch in flight. The last CTA of a
-// launch to finish re-arms its pair, so a pair is clean when the ring comes round to it again (and on graph replays).
-constexpr int kSchedSlots = 64;
-__device__ unsigned int g_sched[kSchedSlots][2];
 
 struct MmaParams {
   LaunchParams base;
@@ -173,13 +166,8 @@ __global__ void __launch_bounds__(kThreads, 2) accumulate_mma_kernel(const __gri
   const uint32_t bars = sP_u32 + kPBytes;                             // 8 mbarriers + the TMEM base address
   const uint32_t full0 = bars, empty0 = bars + 16, tfull0 = bars + 32, tempty0 = bars + 48;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + kStages * kStageBytes + kPBytes + 64);
-  volatile int* tile_slot = reinterpret_cast<volatile int*>(gen + kStages * kStageBytes + kPBytes + 72);   // [kStages]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // sched_slot < 0 (launches captured into a CUDA graph, whose replays could collide with live launches on a ring
-  // slot): static contiguous partition instead of the shared counter.
-  const bool dynamic = P.sched_slot >= 0;
-  unsigned int* sched = g_sched[dynamic ? P.sched_slot : 0];
   const int per = P.total_tiles / gridDim.x, rem = P.total_tiles % gridDim.x;
   const int first = blockIdx.x * per + min((int)blockIdx.x, rem);
   const int count = per + ((int)blockIdx.x < rem ? 1 : 0);
@@ -215,23 +203,13 @@ __global__ void __launch_bounds__(kThreads, 2) accumulate_mma_kernel(const __gri
 
   if (warp == 4) {
     // ===== TMA producer =====
-    // Tiles are claimed one at a time from the launch-wide counter (CTAs on the slower die / behind a slow first
-    // load simply claim fewer), and announced to the other roles through tile_slot[stage]; -1 ends the stream.
     if (lane == 0) {
       int li = 0;
-      for (int i = 0;; ++i) {
+      for (int i = 0; i < count; ++i) {
+        const Tile t = decode_tile(P, first + i, li);
         const int s = i % kStages;
         const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-        int tile = dynamic ? (int)atomicAdd(&sched[0], 1u) : (i < count ? first + i : P.total_tiles);
-        if (tile >= P.total_tiles) tile = -1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);            // the MMAs of iteration i-2 have read this stage
-        mbar_wait(tempty0 + 8 * s, ph ^ 1u);           // the epilogue of iteration i-2 has taken its tile_slot
-        tile_slot[s] = tile;
-        if (tile < 0) {
-          mbar_arrive(full0 + 8 * s);                  // completes the phase without any bytes
-          break;
-        }
-        const Tile t = decode_tile(P, tile, li);
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
         mbar_expect_tx(full0 + 8 * s, kStageBytes);
         const uint32_t q_dst = base + s * kStageBytes, k_dst = q_dst + kQBytes;
         tma_load_4d(&MP.qmap[t.li], full0 + 8 * s, q_dst, 0, t.head, t.pixel0, t.prompt);
@@ -242,14 +220,12 @@ __global__ void __launch_bounds__(kThreads, 2) accumulate_mma_kernel(const __gri
     // ===== MMA issuer =====
     if (lane == 0) {
       int li = 0;
-      for (int i = 0;; ++i) {
+      for (int i = 0; i < count; ++i) {
+        const Tile t = decode_tile(P, first + i, li);
         const int s = i % kStages, a = i & 1;
         const uint32_t ph = (uint32_t)(i / kStages) & 1u, aph = (uint32_t)(i >> 1) & 1u;
         mbar_wait(tempty0 + 8 * a, aph ^ 1u);          // epilogue has drained this accumulator
-        mbar_wait(full0 + 8 * s, ph);                  // TMA bytes have landed (or the end marker)
-        const int tile = tile_slot[s];
-        if (tile < 0) break;
-        const Tile t = decode_tile(P, tile, li);
+        mbar_wait(full0 + 8 * s, ph);                  // TMA bytes have landed
         tc_fence_after();
         const uint32_t q_src = base + s * kStageBytes, k_src = q_src + kQBytes;
         const uint32_t idesc = umma_idesc(P.layer[t.li].dtype == DAAM_BF16);
@@ -266,14 +242,11 @@ __global__ void __launch_bounds__(kThreads, 2) accumulate_mma_kernel(const __gri
     int li = 0;
     const int tid = threadIdx.x;                       // 0..127 == pixel within the tile == TMEM lane
     bool issued = false;
-    for (int i = 0;; ++i) {
+    for (int i = 0; i < count; ++i) {
+      const Tile t = decode_tile(P, first + i, li);
+      const LayerParams& L = P.layer[t.li];
       const int a = i & 1;
       const uint32_t aph = (uint32_t)(i >> 1) & 1u;
-      mbar_wait(full0 + 8 * a, aph);                   // producer's tile_slot[a] for this iteration is published
-      const int tile = tile_slot[a];
-      if (tile < 0) break;
-      const Tile t = decode_tile(P, tile, li);
-      const LayerParams& L = P.layer[t.li];
       mbar_wait(tfull0 + 8 * a, aph);
       tc_fence_after();
       float v[kTokensPad];
@@ -331,14 +304,6 @@ __global__ void __launch_bounds__(kThreads, 2) accumulate_mma_kernel(const __gri
 
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0 && dynamic) {
-    __threadfence();
-    if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) {   // last CTA out: clean pair for the next user of this slot
-      sched[0] = 0u;
-      sched[1] = 0u;
-      __threadfence();
-    }
-  }
   if (warp == 5) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
@@ -449,14 +414,7 @@ bool mma_supported(const LayerParams& L) {
 int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStream_t stream) {
   if (dev.cc_major != 10) { set_error("the tcgen05 kernel needs an sm_100 device (found sm_%d%d)", dev.cc_major, dev.cc_minor); return DAAM_E_UNSUPPORTED; }
   static thread_local MmaParams mp;
-  static std::atomic<unsigned> launch_seq{0};
   mp.base = p;
-  // Inside a stream capture the launch becomes a plain kernel node (programmatic edges are left to the graph owner)
-  // with a static tile partition (see the kernel).
-  cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
-  DAAM_CUDA_TRY(cudaStreamIsCapturing(stream, &capture));
-  const bool capturing = capture != cudaStreamCaptureStatusNone;
-  mp.base.sched_slot = capturing || p.static_tiles ? -1 : (int)(launch_seq.fetch_add(1, std::memory_order_relaxed) % kSchedSlots);
   for (int i = 0; i < p.n_layers; ++i) {
     const LayerParams& L = p.layer[i];
     if (int rc = make_qk_map(L.q, L.dtype, L.heads, L.hw, L.n_prompts, L.qs_head, L.qs_pixel, L.qs_prompt, kTilePixels, &mp.qmap[i])) return rc;
@@ -475,9 +433,12 @@ int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStre
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
+  // Inside a stream capture the launch becomes a plain kernel node (programmatic edges are left to the graph owner).
+  cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+  DAAM_CUDA_TRY(cudaStreamIsCapturing(stream, &capture));
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = (p.pdl && !capturing) ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (p.pdl && capture == cudaStreamCaptureStatusNone) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel, mp));

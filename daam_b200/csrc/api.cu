@@ -96,8 +96,6 @@ extern "C" int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint3
   mma.rmw_mode = (rmw == DAAM_ACC_RMW_LDST) ? 0 : 1;      // default: reduce-add (bulk tensor reduce / red.global)
   simt.rmw_mode = (rmw == DAAM_ACC_RMW_LDST) ? 0 : 1;
   mma.pdl = simt.pdl = (flags & DAAM_ACC_NO_PDL) ? 0 : 1;
-  mma.static_tiles = simt.static_tiles = (flags & DAAM_ACC_STATIC_TILES) ? 1 : 0;
-  mma.sched_slot = simt.sched_slot = -1;
   auto flush = [&](LaunchParams& p, bool is_mma) -> int {
     if (p.n_layers == 0) return DAAM_OK;
     int rc = is_mma ? launch_accumulate_mma(p, dev, stream) : launch_accumulate_simt(p, dev, stream);

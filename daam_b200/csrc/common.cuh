@@ -36,8 +36,6 @@ struct LaunchParams {
   int total_tiles;
   int rmw_mode;             // 0: load/add/store, 1: reduce-add
   int pdl;                  // 1: launch with programmatic stream serialization (prologue overlaps the previous kernel)
-  int sched_slot;           // tcgen05 kernel: pair of the dynamic tile scheduler ring used by this launch, -1: static
-  int static_tiles;         // 1: caller asked for the static tile partition (DAAM_ACC_STATIC_TILES)
   LayerParams layer[kMaxLayersPerLaunch];
 };
 

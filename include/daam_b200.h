@@ -47,7 +47,6 @@ enum daam_dtype { DAAM_F32 = 0, DAAM_F16 = 1, DAAM_BF16 = 2 };
 #define DAAM_ACC_RMW_LDST   0x10u /* coalesced load / add / store of the accumulator tile */
 #define DAAM_ACC_RMW_RED    0x20u /* red.global.add.f32 (SIMT) / bulk-async reduce-add from shared memory (MMA) */
 #define DAAM_ACC_NO_PDL     0x100u /* launch without programmatic dependent launch (measurement / debugging) */
-#define DAAM_ACC_STATIC_TILES 0x200u /* tcgen05 path: static tile partition instead of the dynamic scheduler */
 
 /*
  * One traced cross-attention layer call: the conditional half of the projections `to_q(hidden_states)` and

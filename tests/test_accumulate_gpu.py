@@ -21,7 +21,6 @@ PATHS = [
     ('simt-red', _native.ACC_FORCE_SIMT | _native.ACC_RMW_RED),
     ('mma-red', _native.ACC_FORCE_MMA | _native.ACC_RMW_RED),
     ('mma-ldst', _native.ACC_FORCE_MMA | _native.ACC_RMW_LDST),
-    ('mma-static', _native.ACC_FORCE_MMA | _native.ACC_STATIC_TILES),
     ('auto', _native.ACC_AUTO),
 ]
 

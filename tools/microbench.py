@@ -54,7 +54,6 @@ def main():
         'mma-red': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED,
         'mma-ldst': _native.ACC_FORCE_MMA | _native.ACC_RMW_LDST,
         'mma-red-nopdl': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED | _native.ACC_NO_PDL,
-        'mma-red-static': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED | _native.ACC_STATIC_TILES,
     }
     if args.variants:
         variants = {k: v for k, v in variants.items() if k in args.variants}
