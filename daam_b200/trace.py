@@ -65,6 +65,8 @@ class DiffusionHeatMapHooker(AggregateHooker):
         self._pending: List[tuple] = []        # (layer_idx, DaamLayer, q, k, acc) awaiting the step launch
         self._pending_layers = set()
         self._desc_cache: Dict[int, tuple] = {}
+        self._packed = None                    # reusable host-side daam_layer[] for the step launch
+        self._inflight: List[tuple] = []       # (event, projections) of step launches that may still be running
         self._stream: Optional[torch.cuda.Stream] = None
         self._dirty = False                    # side-stream work not yet ordered before the current stream
         self.all_heat_maps.bind(self.synchronize, self._zero_slabs)
@@ -107,7 +109,7 @@ class DiffusionHeatMapHooker(AggregateHooker):
             self._forward_hook = unet.register_forward_hook(lambda *_: self.flush())
 
     def _unhook_impl(self):
-        self.flush()
+        self.synchronize()      # issue what is queued and order it (and the parked projections) before the caller's stream
         if getattr(self, '_forward_hook', None) is not None:
             self._forward_hook.remove()
             self._forward_hook = None
@@ -120,23 +122,27 @@ class DiffusionHeatMapHooker(AggregateHooker):
         return self._stream
 
     def _enqueue(self, layer_idx: int, factor: int, q: torch.Tensor, k: torch.Tensor, heads: int, scale: float):
-        """Register one traced layer call: ``q [B, hw, C]``, ``k [B, 77, C]`` straight from ``to_q`` / ``to_k``."""
+        """Register one traced layer call: ``q [B, hw, C]``, ``k [B, 77, C]`` straight from ``to_q`` / ``to_k``.
+
+        This runs once per layer per step on the host's critical path, so the steady state does as little as possible:
+        when the projections are contiguous and shaped like the layer's previous call, only the two data pointers of
+        the cached ``daam_layer`` change."""
         if layer_idx in self._pending_layers:   # the layer comes round again: a new UNet forward has started
             self.flush()
-        if q.stride(-1) != 1 or k.stride(-1) != 1:
-            q, k = q.contiguous(), k.contiguous()
-        # Steady state: same shapes/strides as the last call of this layer -> only the two data pointers change.
-        sig = (q.shape, q.stride(), k.shape, k.stride(), q.dtype, q.device, heads, factor)
         cached = self._desc_cache.get(layer_idx)
-        if cached is not None and cached[0] == sig and self.all_heat_maps.slabs.get(layer_idx) is cached[2]:
-            _, desc, slab, q_off, k_off = cached
+        if cached is not None and q.shape == cached[0] and q.dtype is cached[1] and q.is_contiguous() \
+                and k.is_contiguous() and self.all_heat_maps.slabs.get(layer_idx) is cached[3]:
+            _, _, desc, slab, q_off, k_off = cached
             desc.q = q.data_ptr() + q_off
             desc.k = k.data_ptr() + k_off
-            self.all_heat_maps.mark_live(slab)
+            if not slab.touched:
+                self.all_heat_maps.mark_live(slab)
         else:
             if not q.is_cuda:
                 raise RuntimeError('daam_b200 traces pipelines that live on a CUDA device only (there is no CPU '
                                    'fallback)')
+            if q.stride(-1) != 1 or k.stride(-1) != 1:
+                q, k = q.contiguous(), k.contiguous()
             bsz, hw, _ = q.shape
             side = int(math.sqrt(hw))
             if side * side != hw:
@@ -147,13 +153,15 @@ class DiffusionHeatMapHooker(AggregateHooker):
                 raise ValueError('Only single prompt generation is supported for heat map computation.')
             slab = self.all_heat_maps.slab_for(layer_idx, factor, n_prompts, n_heads, side, side, q.device, head0)
             desc = ops.make_layer_desc(q, k, slab.acc, heads, scale)
-            self._desc_cache[layer_idx] = (sig, desc, slab, desc.q - q.data_ptr(), desc.k - k.data_ptr())
-        if torch.cuda.is_current_stream_capturing():
-            slab.captured = True
+            # the fast path above is only valid for contiguous projections (strides implied by the shape)
+            shape_key = q.shape if (q.is_contiguous() and k.is_contiguous()) else None
+            self._desc_cache[layer_idx] = (shape_key, q.dtype, desc, slab, desc.q - q.data_ptr(), desc.k - k.data_ptr())
         if self.launch == 'layer':
+            if torch.cuda.is_current_stream_capturing():
+                slab.captured = True
             ops.accumulate([desc], q.device, flags=self.kernel_flags)
             return
-        self._pending.append((layer_idx, desc, q, k, slab.acc))   # tensors kept alive until the launch
+        self._pending.append((layer_idx, desc, q, k, slab))   # tensors kept alive until the launch
         self._pending_layers.add(layer_idx)
 
     def _accumulate_probs(self, layer_idx: int, factor: int, probs: torch.Tensor, bsz: int, heads: int):
@@ -169,22 +177,34 @@ class DiffusionHeatMapHooker(AggregateHooker):
 
     def flush(self):
         """Issue the queued layer calls as one persistent launch on the side stream."""
-        if not self._pending:
+        pending = self._pending
+        if not pending:
             return
-        device = self._pending[0][2].device
-        descs = [p[1] for p in self._pending]
+        device = pending[0][2].device
+        n = len(pending)
+        packed = self._packed
+        if packed is None or len(packed.array) < n:
+            packed = self._packed = _native.PackedLayers([_native.DaamLayer()] * max(n, 64))
+        for i, item in enumerate(pending):            # struct copies into the reusable host array
+            packed.array[i] = item[1]
+        packed.n = n
         if torch.cuda.is_current_stream_capturing():
             # CUDA-graph capture of the UNet step: the launch becomes a node of the captured stream itself
-            ops.accumulate(descs, device, flags=self.kernel_flags)
+            for item in pending:
+                item[4].captured = True
+            ops.accumulate(packed, device, flags=self.kernel_flags)
         else:
             side = self._side_stream(device)
             side.wait_stream(torch.cuda.current_stream(device))   # Q/K were produced on the current stream
-            ops.accumulate(descs, device, stream=side, flags=self.kernel_flags)
-            for _, _, q, k, _ in self._pending:                     # keep the projections alive until the kernel ran
-                q.record_stream(side)
-                k.record_stream(side)
+            ops.accumulate(packed, device, stream=side, flags=self.kernel_flags)
+            # Keep the projections alive until the kernel has run: park the references behind an event instead of
+            # 2 x n_layers record_stream calls; batches whose event has fired are dropped here, one step later.
+            done = torch.cuda.Event()
+            done.record(side)
+            self._inflight = [b for b in self._inflight if not b[0].query()]
+            self._inflight.append((done, [(item[2], item[3]) for item in pending]))
             self._dirty = True
-        self._pending.clear()
+        self._pending = []
         self._pending_layers.clear()
 
     def synchronize(self):
@@ -193,6 +213,9 @@ class DiffusionHeatMapHooker(AggregateHooker):
         if self._dirty and self._stream is not None:
             torch.cuda.current_stream(self._stream.device).wait_stream(self._stream)
             self._dirty = False
+            # parked projections: their memory may only be reused by the current stream after the side stream is done
+            # with them, which the wait above now guarantees for everything issued so far
+            self._inflight = []
 
     def _zero_slabs(self, slabs: List[LayerSlab]):
         if not slabs:
@@ -367,7 +390,6 @@ class UNetCrossAttentionHooker(ObjectHooker):
         out = out.view(bsz, heads, n, d).permute(0, 2, 1, 3).reshape(bsz, n, heads * d)
         return attn.to_out[1](attn.to_out[0](out))
 
-    @torch.no_grad()
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None):
         """attn2 forward: projections -> (heat-map kernel on Q/K) -> SDPA -> output projection."""
         if attention_mask is not None:
