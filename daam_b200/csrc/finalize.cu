@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
 // loads and 20 FMAs per output for the generic gather. When a class has fewer source pixels per band than threads, the
 // spare thread groups take every kg-th key and the groups are merged through the shared-memory band in a fixed order
 // (deterministic sums). Arithmetic per key is bit-identical to bicubic_at (same taps, same weights, same order).
-constexpr int kBandRows = 16;
+constexpr int kBandRows = 8;
+constexpr int kMaxClassKeys = 2048;        // key pointers of one class staged in shared memory
 
 template <int F>
 struct PhaseWeights {
@@ -122,13 +123,68 @@ struct PhaseWeights {
   }
 };
 
+// Fills keys[] (shared) with the source pointer (token row t) of every selected key of the class; returns the count.
+__device__ __forceinline__ int stage_class_keys(const FinalizeParams& P, int cls_side, int t, const float** keys) {
+  __shared__ int n_keys_s;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int g = 0; g < P.n_groups; ++g) {
+      const daam_key_group& G = P.g[g];
+      if (G.h != cls_side || G.w != cls_side) continue;
+      const int h0 = G.head_sel < 0 ? 0 : G.head_sel;
+      const int h1 = G.head_sel < 0 ? G.heads : G.head_sel + 1;
+      const long long hw = (long long)G.h * G.w;
+      for (int head = h0; head < h1; ++head) keys[n++] = G.acc + ((long long)head * G.tokens + t) * hw;
+    }
+    n_keys_s = n;
+  }
+  __syncthreads();
+  return n_keys_s;
+}
+
 template <int F>
-__device__ __forceinline__ void class_pass(const FinalizeParams& P, int cls_h, int t, int band, float* tile) {
+__device__ __forceinline__ void load_window(const float* src, const int (&iy)[5], const int (&ix)[5], float (&v)[5][5]) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) v[i][j] = __ldg(src + iy[i] + ix[j]);
+}
+
+template <int F>
+__device__ __forceinline__ void add_key(const PhaseWeights<F>& pw, const float (&v)[5][5], float (&acc)[F][F]) {
+  float r[5][F];                                       // horizontal pass, per source row and output phase
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int px = 0; px < F; ++px) {
+      const int off = px < F / 2 ? 0 : 1;
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q += pw.w[px][j] * v[i][off + j];
+      r[i][px] = q;
+    }
+#pragma unroll
+  for (int py = 0; py < F; ++py) {
+    const int off = py < F / 2 ? 0 : 1;
+#pragma unroll
+    for (int px = 0; px < F; ++px) {
+      float o = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o += pw.w[py][i] * r[off + i][px];
+      acc[py][px] += fmaxf(o, 0.f);
+    }
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void class_pass(const FinalizeParams& P, int cls_h, int t, int band, float* tile,
+                                           const float** keys) {
   constexpr int R = kBandRows / F;                     // source rows under this band
   const int x = P.x, w = cls_h, h = cls_h;
   const int n_src = R * w;
   const int kg = n_src >= 256 ? 1 : 256 / n_src;       // thread groups that split the keys
   const int passes = (n_src + 255) / 256;
+  const int nk = stage_class_keys(P, cls_h, t, keys);
   PhaseWeights<F> pw;
   pw.init();
   for (int pass = 0; pass < passes; ++pass) {
@@ -148,45 +204,16 @@ __device__ __forceinline__ void class_pass(const FinalizeParams& P, int cls_h, i
 #pragma unroll
       for (int px = 0; px < F; ++px) acc[py][px] = 0.f;
     if (live) {
-      int k = 0;
-      for (int g = 0; g < P.n_groups; ++g) {
-        const daam_key_group& G = P.g[g];
-        if (G.h != cls_h || G.w != cls_h) continue;
-        const int h0 = G.head_sel < 0 ? 0 : G.head_sel;
-        const int h1 = G.head_sel < 0 ? G.heads : G.head_sel + 1;
-        const long long head_stride = (long long)G.tokens * h * w;
-        const float* base = G.acc + (long long)t * h * w;
-        for (int head = h0; head < h1; ++head, ++k) {
-          if (k % kg != group) continue;
-          const float* src = base + head * head_stride;
-          float v[5][5];
-#pragma unroll
-          for (int i = 0; i < 5; ++i)
-#pragma unroll
-            for (int j = 0; j < 5; ++j) v[i][j] = __ldg(src + iy[i] + ix[j]);
-          float r[5][F];                               // horizontal pass, per source row and output phase
-#pragma unroll
-          for (int i = 0; i < 5; ++i)
-#pragma unroll
-            for (int px = 0; px < F; ++px) {
-              const int off = px < F / 2 ? 0 : 1;
-              float q = 0.f;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) q += pw.w[px][j] * v[i][off + j];
-              r[i][px] = q;
-            }
-#pragma unroll
-          for (int py = 0; py < F; ++py) {
-            const int off = py < F / 2 ? 0 : 1;
-#pragma unroll
-            for (int px = 0; px < F; ++px) {
-              float o = 0.f;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) o += pw.w[py][i] * r[off + i][px];
-              acc[py][px] += fmaxf(o, 0.f);
-            }
-          }
-        }
+      // two windows in flight: the loads of the next key are issued before the arithmetic of the current one
+      float va[5][5], vb[5][5];
+      int k = group;
+      if (k < nk) load_window<F>(keys[k], iy, ix, va);
+      for (; k < nk; k += 2 * kg) {
+        const bool has_b = k + kg < nk;
+        if (has_b) load_window<F>(keys[k + kg], iy, ix, vb);
+        add_key<F>(pw, va, acc);
+        if (k + 2 * kg < nk) load_window<F>(keys[k + 2 * kg], iy, ix, va);
+        if (has_b) add_key<F>(pw, vb, acc);
       }
     }
     for (int g = 0; g < kg; ++g) {                      // merge the key groups in a fixed order
@@ -202,31 +229,38 @@ __device__ __forceinline__ void class_pass(const FinalizeParams& P, int cls_h, i
   }
 }
 
-// factor 1: bicubic at scale 1 is the identity, the class contributes clamp(src) -- coalesced float4 reads
-__device__ __forceinline__ void class_pass_identity(const FinalizeParams& P, int t, int band, float* tile) {
+// factor 1: bicubic at scale 1 is the identity, the class contributes clamp(src) -- coalesced float4 reads; when the
+// band has fewer float4s than threads, the spare thread groups take every kg-th key (merged in a fixed order)
+__device__ __forceinline__ void class_pass_identity(const FinalizeParams& P, int t, int band, float* tile,
+                                                    const float** keys) {
   const int x = P.x;
   const int n4 = kBandRows * x / 4;
-  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+  const int nk = stage_class_keys(P, x, t, keys);
+  const int kg = n4 >= 256 ? 1 : 256 / n4;
+  const int passes = (n4 + 255) / 256;
+  for (int pass = 0; pass < passes; ++pass) {
+    const int group = n4 >= 256 ? 0 : (int)threadIdx.x / n4;
+    const int i = n4 >= 256 ? pass * 256 + (int)threadIdx.x : (int)threadIdx.x % n4;
+    const bool live = i < n4 && group < kg;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const long long off = (long long)t * x * x + (long long)band * kBandRows * x + 4 * i;
-    for (int g = 0; g < P.n_groups; ++g) {
-      const daam_key_group& G = P.g[g];
-      if (G.h != x || G.w != x) continue;
-      const int h0 = G.head_sel < 0 ? 0 : G.head_sel;
-      const int h1 = G.head_sel < 0 ? G.heads : G.head_sel + 1;
-      const long long head_stride = (long long)G.tokens * x * x;
+    if (live) {
+      const long long off = (long long)band * kBandRows * x + 4 * i;
 #pragma unroll 4
-      for (int head = h0; head < h1; ++head) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(G.acc + head * head_stride + off));
+      for (int k = group; k < nk; k += kg) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(keys[k] + off));
         acc.x += fmaxf(v.x, 0.f); acc.y += fmaxf(v.y, 0.f); acc.z += fmaxf(v.z, 0.f); acc.w += fmaxf(v.w, 0.f);
       }
     }
-    float4* dst = reinterpret_cast<float4*>(tile + 4 * i);
-    float4 cur = *dst;
-    cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
-    *dst = cur;
+    for (int g = 0; g < kg; ++g) {
+      if (live && group == g) {
+        float4* dst = reinterpret_cast<float4*>(tile + 4 * i);
+        float4 cur = *dst;
+        cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
+        *dst = cur;
+      }
+      __syncthreads();
+    }
   }
-  __syncthreads();
 }
 
 struct ClassList {
@@ -234,19 +268,20 @@ struct ClassList {
   int side[8];      // distinct source sides, all dividing x with factor 1, 2 or 4
 };
 
-// grid: (x / 16 bands, n_rows); dynamic smem: 16 * x floats
+// grid: (x / kBandRows bands, n_rows); dynamic smem: kBandRows * x floats
 __global__ void __launch_bounds__(256) finalize_fast_kernel(const __grid_constant__ FinalizeParams P,
                                                             const __grid_constant__ ClassList C,
                                                             float* __restrict__ out) {
   extern __shared__ __align__(16) float tile[];
+  __shared__ const float* keys[kMaxClassKeys];
   const int band = blockIdx.x, t = blockIdx.y, x = P.x;
   for (int i = threadIdx.x; i < kBandRows * x; i += blockDim.x) tile[i] = 0.f;
   __syncthreads();
   for (int c = 0; c < C.n; ++c) {
     const int side = C.side[c], f = x / side;
-    if (f == 1) class_pass_identity(P, t, band, tile);
-    else if (f == 2) class_pass<2>(P, side, t, band, tile);
-    else class_pass<4>(P, side, t, band, tile);
+    if (f == 1) class_pass_identity(P, t, band, tile, keys);
+    else if (f == 2) class_pass<2>(P, side, t, band, tile, keys);
+    else class_pass<4>(P, side, t, band, tile, keys);
   }
   float* dst = out + (long long)t * x * x + (long long)band * kBandRows * x;
   for (int i = threadIdx.x; i < kBandRows * x; i += blockDim.x) dst[i] = tile[i] / (float)P.n_keys;
@@ -388,7 +423,7 @@ extern "C" int daam_finalize(const daam_key_group* groups, int32_t n_groups, int
   // fast path: every key is square with an integer factor 1 / 2 / 4 (all SD / SDXL layers that are ever traced)
   ClassList cls;
   cls.n = 0;
-  bool fast = x % kBandRows == 0 && x % 4 == 0 && x <= 256 && !force_generic_finalize();
+  bool fast = x % kBandRows == 0 && x % 4 == 0 && x <= 256 && p.n_keys <= kMaxClassKeys && !force_generic_finalize();
   for (int i = 0; i < n_groups && fast; ++i) {
     const daam_key_group& g = groups[i];
     if (g.h != g.w || x % g.h != 0 || (x / g.h != 1 && x / g.h != 2 && x / g.h != 4) ||
