@@ -16,6 +16,13 @@
 // Warp roles: 0-3 epilogue, 4 TMA producer (one elected thread), 5 TMEM allocator + MMA issuer (one thread).
 // Persistent: every CTA walks a contiguous chunk of the launch's tiles; up to 2 CTAs per SM (256 TMEM columns each).
 //
+// fp32 projections (the reference's default dtype for SD-1.x/2.x, daam/run/generate.py:205) take the same kernel in
+// "split" form: tensor cores have no fp32 operand type and kind::tf32 would drop 13 mantissa bits, so four converter
+// warps load the fp32 Q/K tiles with coalesced 16-byte loads, split every value into three bf16 terms
+// (x = x1 + x2 + x3 carries all 24 significand bits), store them as three swizzled operand tiles each, and the MMA
+// warp accumulates the six products of order <= 2^-16 (q1k1 + q1k2 + q2k1 + q1k3 + q2k2 + q3k1) in fp32 in TMEM:
+// 24 MMAs per tile instead of 4, still far from the tensor pipe's limit, and the path stays HBM-bound.
+//
 // Replaces daam/trace.py:276 (get_attention_scores), :219-244 (_unravel_attn) and :293-294 (update loop).
 #include <cuda.h>
 
@@ -37,6 +44,10 @@ constexpr int kTmemCols = 256;
 constexpr int kAccCols = 128;                         // column distance between the two accumulators
 constexpr int kThreads = 192;
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kPBytes + 128;
+// split (fp32) form: a stage holds Q1 Q2 Q3 K1 K2 K3; warps 6-9 convert; one CTA per SM
+constexpr int kSplitStageBytes = 3 * kStageBytes;
+constexpr int kSplitThreads = 320;
+constexpr int kSplitSmemBytes = 1024 + kStages * kSplitStageBytes + kPBytes + 128;
 
 struct MmaParams {
   LaunchParams base;
@@ -155,17 +166,70 @@ __device__ __forceinline__ Tile decode_tile(const LaunchParams& P, int tile, int
   return t;
 }
 
-__global__ void __launch_bounds__(kThreads, 2) accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
+// fp32 -> three bf16 terms, 8 values -> one 16-byte chunk per term
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& p1, uint4& p2, uint4& p3) {
+  __nv_bfloat162 a[4], b[4], c[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float lo = x[2 * i], hi = x[2 * i + 1];
+    const __nv_bfloat16 a0 = __float2bfloat16_rn(lo), a1 = __float2bfloat16_rn(hi);
+    lo -= __bfloat162float(a0); hi -= __bfloat162float(a1);
+    const __nv_bfloat16 b0 = __float2bfloat16_rn(lo), b1 = __float2bfloat16_rn(hi);
+    lo -= __bfloat162float(b0); hi -= __bfloat162float(b1);
+    a[i] = __halves2bfloat162(a0, a1);
+    b[i] = __halves2bfloat162(b0, b1);
+    c[i] = __halves2bfloat162(__float2bfloat16_rn(lo), __float2bfloat16_rn(hi));
+  }
+  p1 = *reinterpret_cast<uint4*>(a);
+  p2 = *reinterpret_cast<uint4*>(b);
+  p3 = *reinterpret_cast<uint4*>(c);
+}
+
+// Converter warps (split form): rows [row0, row0 + n_rows_live) of a fp32 [rows x 64] operand -> three 128B-swizzled
+// K-major bf16 tiles at dst, dst + part_bytes, dst + 2 * part_bytes. `n_chunks` 16-byte chunks (8 floats) in total,
+// chunk = row * 8 + group; rows >= n_rows_live are written as zeros. ctid: 0..127.
+template <int kChunksPerThread>
+__device__ __forceinline__ void convert_operand(const float* src_base, long long row_stride, int n_rows_live,
+                                                uint8_t* dst, int part_bytes, int ctid) {
+  float4 lo[kChunksPerThread], hi[kChunksPerThread];
+#pragma unroll
+  for (int c = 0; c < kChunksPerThread; ++c) {            // all loads first: 2 x kChunksPerThread in flight per thread
+    const int chunk = ctid + 128 * c, r = chunk >> 3, g = chunk & 7;
+    if (r < n_rows_live) {
+      const float4* srcp = reinterpret_cast<const float4*>(src_base + (long long)r * row_stride + g * 8);
+      lo[c] = __ldg(srcp);
+      hi[c] = __ldg(srcp + 1);
+    } else {
+      lo[c] = hi[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kChunksPerThread; ++c) {
+    const int chunk = ctid + 128 * c, r = chunk >> 3, g = chunk & 7;
+    const float x[8] = {lo[c].x, lo[c].y, lo[c].z, lo[c].w, hi[c].x, hi[c].y, hi[c].z, hi[c].w};
+    uint4 p1, p2, p3;
+    split8(x, p1, p2, p3);
+    const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((g ^ (r & 7)) << 4);     // SWIZZLE_128B, K-major
+    *reinterpret_cast<uint4*>(dst + off) = p1;
+    *reinterpret_cast<uint4*>(dst + part_bytes + off) = p2;
+    *reinterpret_cast<uint4*>(dst + 2 * part_bytes + off) = p3;
+  }
+}
+
+template <bool kSplit>
+__global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, kSplit ? 1 : 2)
+accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
+  constexpr int kStageBytesT = kSplit ? kSplitStageBytes : kStageBytes;
   const LaunchParams& P = MP.base;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                       // 1024-byte alignment for the swizzled tiles
   uint8_t* gen = smem_raw + (base - raw);
-  float* sP = reinterpret_cast<float*>(gen + kStages * kStageBytes);
-  const uint32_t sP_u32 = base + kStages * kStageBytes;
+  float* sP = reinterpret_cast<float*>(gen + kStages * kStageBytesT);
+  const uint32_t sP_u32 = base + kStages * kStageBytesT;
   const uint32_t bars = sP_u32 + kPBytes;                             // 8 mbarriers + the TMEM base address
   const uint32_t full0 = bars, empty0 = bars + 16, tfull0 = bars + 32, tempty0 = bars + 48;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + kStages * kStageBytes + kPBytes + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + kStages * kStageBytesT + kPBytes + 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = P.total_tiles / gridDim.x, rem = P.total_tiles % gridDim.x;
@@ -175,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 2) accumulate_mma_kernel(const __gri
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full0 + 8 * s, 1);
+      mbar_init(full0 + 8 * s, kSplit ? 128 : 1);   // split form: one arrival per converter thread
       mbar_init(empty0 + 8 * s, 1);
     }
 #pragma unroll
@@ -201,9 +265,28 @@ __global__ void __launch_bounds__(kThreads, 2) accumulate_mma_kernel(const __gri
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  if (warp == 4) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+  if (kSplit && warp >= 6) {
+    // ===== converter warps (fp32 projections): global fp32 -> three bf16 operand tiles per operand =====
+    const int ctid = threadIdx.x - 192;
+    int li = 0;
+    for (int i = 0; i < count; ++i) {
+      const Tile t = decode_tile(P, first + i, li);
+      const LayerParams& L = P.layer[t.li];
+      const int s = i % kStages;
+      const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+      mbar_wait(empty0 + 8 * s, ph ^ 1u);
+      uint8_t* stage = gen + s * kStageBytesT;
+      const float* qsrc = static_cast<const float*>(L.q) + t.prompt * L.qs_prompt + t.head * L.qs_head +
+                          (long long)t.pixel0 * L.qs_pixel;
+      const float* ksrc = static_cast<const float*>(L.k) + t.prompt * L.ks_prompt + t.head * L.ks_head;
+      convert_operand<8>(qsrc, L.qs_pixel, min(kTilePixels, L.hw - t.pixel0), stage, kQBytes, ctid);
+      convert_operand<5>(ksrc, L.ks_token, kTokens, stage + 3 * kQBytes, kKBytes, ctid);
+      fence_proxy_async();                             // generic-proxy stores -> visible to the tensor core's reads
+      mbar_arrive(full0 + 8 * s);
+    }
+  } else if (warp == 4) {
+    // ===== TMA producer (16-bit projections) =====
+    if (!kSplit && lane == 0) {
       int li = 0;
       for (int i = 0; i < count; ++i) {
         const Tile t = decode_tile(P, first + i, li);
@@ -211,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 2) accumulate_mma_kernel(const __gri
         const uint32_t ph = (uint32_t)(i / kStages) & 1u;
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
         mbar_expect_tx(full0 + 8 * s, kStageBytes);
-        const uint32_t q_dst = base + s * kStageBytes, k_dst = q_dst + kQBytes;
+        const uint32_t q_dst = base + s * kStageBytesT, k_dst = q_dst + kQBytes;
         tma_load_4d(&MP.qmap[t.li], full0 + 8 * s, q_dst, 0, t.head, t.pixel0, t.prompt);
         tma_load_4d(&MP.kmap[t.li], full0 + 8 * s, k_dst, 0, t.head, 0, t.prompt);
       }
@@ -227,17 +310,31 @@ __global__ void __launch_bounds__(kThreads, 2) accumulate_mma_kernel(const __gri
         mbar_wait(tempty0 + 8 * a, aph ^ 1u);          // epilogue has drained this accumulator
         mbar_wait(full0 + 8 * s, ph);                  // TMA bytes have landed
         tc_fence_after();
-        const uint32_t q_src = base + s * kStageBytes, k_src = q_src + kQBytes;
-        const uint32_t idesc = umma_idesc(P.layer[t.li].dtype == DAAM_BF16);
+        const uint32_t q_src = base + s * kStageBytesT;
         const uint32_t d_tmem = tmem_base + a * kAccCols;
+        if constexpr (kSplit) {
+          // q.k = sum of the six split products up to order 2^-16, smallest first; every operand is bf16
+          const uint32_t k_src = q_src + 3 * kQBytes;
+          const uint32_t idesc = umma_idesc(true);
+          constexpr int qa[6] = {2, 0, 1, 1, 0, 0}, kb[6] = {0, 2, 1, 0, 1, 0};
 #pragma unroll
-        for (int k = 0; k < 4; ++k)                    // head_dim 64 = 4 x UMMA_K 16 (32 bytes along the swizzled row)
-          umma_f16(d_tmem, umma_desc_sw128(q_src + 32 * k), umma_desc_sw128(k_src + 32 * k), idesc, k > 0);
+          for (int p = 0; p < 6; ++p)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(d_tmem, umma_desc_sw128(q_src + qa[p] * kQBytes + 32 * k),
+                       umma_desc_sw128(k_src + kb[p] * kKBytes + 32 * k), idesc, (p | k) != 0);
+        } else {
+          const uint32_t k_src = q_src + kQBytes;
+          const uint32_t idesc = umma_idesc(P.layer[t.li].dtype == DAAM_BF16);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                  // head_dim 64 = 4 x UMMA_K 16 (32 bytes along the swizzled row)
+            umma_f16(d_tmem, umma_desc_sw128(q_src + 32 * k), umma_desc_sw128(k_src + 32 * k), idesc, k > 0);
+        }
         umma_commit(empty0 + 8 * s);                   // frees the smem stage once the MMAs have read it
         umma_commit(tfull0 + 8 * a);                   // accumulator ready for the epilogue
       }
     }
-  } else {
+  } else if (warp < 4) {
     // ===== epilogue warps: softmax + accumulate =====
     int li = 0;
     const int tid = threadIdx.x;                       // 0..127 == pixel within the tile == TMEM lane
@@ -407,31 +504,35 @@ int make_acc_map(float* acc, int hw, int rows, CUtensorMap* out) {
 }  // namespace
 
 bool mma_supported(const LayerParams& L) {
-  return (L.dtype == DAAM_F16 || L.dtype == DAAM_BF16) && L.head_dim == 64 && L.vec_ok && L.qs_head > 0 &&
-         L.qs_pixel > 0 && L.ks_head > 0 && L.ks_token > 0;
+  return L.head_dim == 64 && L.vec_ok && L.qs_head > 0 && L.qs_pixel > 0 && L.ks_head > 0 && L.ks_token > 0;
 }
 
 int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStream_t stream) {
   if (dev.cc_major != 10) { set_error("the tcgen05 kernel needs an sm_100 device (found sm_%d%d)", dev.cc_major, dev.cc_minor); return DAAM_E_UNSUPPORTED; }
   static thread_local MmaParams mp;
   mp.base = p;
+  const bool split = p.n_layers > 0 && p.layer[0].dtype == DAAM_F32;     // a pack holds one operand class (api.cu)
   for (int i = 0; i < p.n_layers; ++i) {
     const LayerParams& L = p.layer[i];
-    if (int rc = make_qk_map(L.q, L.dtype, L.heads, L.hw, L.n_prompts, L.qs_head, L.qs_pixel, L.qs_prompt, kTilePixels, &mp.qmap[i])) return rc;
-    if (int rc = make_qk_map(L.k, L.dtype, L.heads, kTokens, L.n_prompts, L.ks_head, L.ks_token, L.ks_prompt, kTokensPad, &mp.kmap[i])) return rc;
+    if ((L.dtype == DAAM_F32) != split) { set_error("mixed fp32 / 16-bit layers in one tcgen05 pack"); return DAAM_E_INVALID; }
+    if (!split) {
+      if (int rc = make_qk_map(L.q, L.dtype, L.heads, L.hw, L.n_prompts, L.qs_head, L.qs_pixel, L.qs_prompt, kTilePixels, &mp.qmap[i])) return rc;
+      if (int rc = make_qk_map(L.k, L.dtype, L.heads, kTokens, L.n_prompts, L.ks_head, L.ks_token, L.ks_prompt, kTokensPad, &mp.kmap[i])) return rc;
+    }
     if (int rc = make_acc_map(L.acc, L.hw, L.n_prompts * L.heads * kTokens, &mp.amap[i])) return rc;
   }
   static bool configured = false;
   if (!configured) {
-    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmemBytes));
     configured = true;
   }
-  int grid = dev.sm_count * 2;
+  int grid = dev.sm_count * (split ? 1 : 2);
   if (grid > p.total_tiles) grid = p.total_tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.blockDim = dim3(split ? kSplitThreads : kThreads);
+  cfg.dynamicSmemBytes = split ? kSplitSmemBytes : kSmemBytes;
   cfg.stream = stream;
   // Inside a stream capture the launch becomes a plain kernel node (programmatic edges are left to the graph owner).
   cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
@@ -441,7 +542,8 @@ int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStre
   attr[0].val.programmaticStreamSerializationAllowed = (p.pdl && capture == cudaStreamCaptureStatusNone) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel, mp));
+  if (split) DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<true>, mp));
+  else DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<false>, mp));
   DAAM_CUDA_TRY(cudaGetLastError());
   count_launch();
   return DAAM_OK;

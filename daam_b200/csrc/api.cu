@@ -89,13 +89,13 @@ extern "C" int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint3
   if (int rc = get_device_info(&dev)) return rc;
   const uint32_t path = flags & 3u, rmw = flags & DAAM_ACC_RMW_MASK;
 
-  // Two packs: layers the tcgen05 kernel takes and the rest. Each is flushed when its parameter block is full.
-  static thread_local LaunchParams mma, simt;
-  mma.n_layers = simt.n_layers = 0;
-  mma.total_tiles = simt.total_tiles = 0;
-  mma.rmw_mode = (rmw == DAAM_ACC_RMW_LDST) ? 0 : 1;      // default: reduce-add (bulk tensor reduce / red.global)
-  simt.rmw_mode = (rmw == DAAM_ACC_RMW_LDST) ? 0 : 1;
-  mma.pdl = simt.pdl = (flags & DAAM_ACC_NO_PDL) ? 0 : 1;
+  // Three packs: 16-bit layers for the tcgen05 kernel (TMA form), fp32 layers for its split form, and the rest for
+  // the SIMT kernel. Each is flushed when its parameter block is full.
+  static thread_local LaunchParams mma, mma32, simt;
+  mma.n_layers = mma32.n_layers = simt.n_layers = 0;
+  mma.total_tiles = mma32.total_tiles = simt.total_tiles = 0;
+  mma.rmw_mode = mma32.rmw_mode = simt.rmw_mode = (rmw == DAAM_ACC_RMW_LDST) ? 0 : 1;   // default: reduce-add
+  mma.pdl = mma32.pdl = simt.pdl = (flags & DAAM_ACC_NO_PDL) ? 0 : 1;
   auto flush = [&](LaunchParams& p, bool is_mma) -> int {
     if (p.n_layers == 0) return DAAM_OK;
     int rc = is_mma ? launch_accumulate_mma(p, dev, stream) : launch_accumulate_simt(p, dev, stream);
@@ -112,7 +112,7 @@ extern "C" int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint3
                 L.dtype, L.head_dim, L.vec_ok);
       return DAAM_E_UNSUPPORTED;
     }
-    LaunchParams& p = use_mma ? mma : simt;
+    LaunchParams& p = use_mma ? (L.dtype == DAAM_F32 ? mma32 : mma) : simt;
     L.tile_begin = p.total_tiles;
     p.layer[p.n_layers++] = L;
     p.total_tiles += L.tiles_per_head * L.heads * L.n_prompts;
@@ -120,6 +120,7 @@ extern "C" int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint3
       if (int rc = flush(p, use_mma)) return rc;
   }
   if (int rc = flush(mma, true)) return rc;
+  if (int rc = flush(mma32, true)) return rc;
   if (int rc = flush(simt, false)) return rc;
   return DAAM_OK;
 }

@@ -26,9 +26,10 @@ PATHS = [
 
 
 def skip_unless_mma_applies(path, dtype, head_dim):
-    """The tcgen05 kernel takes 16-bit projections with head_dim 64; forcing it elsewhere is an error by design."""
-    if path.startswith('mma') and (dtype == torch.float32 or head_dim != 64):
-        pytest.skip('tcgen05 path: 16-bit inputs with head_dim 64 only')
+    """The tcgen05 kernel takes head_dim 64 (16-bit operands directly, fp32 as three bf16 terms); forcing it elsewhere
+    is an error by design."""
+    if path.startswith('mma') and head_dim != 64:
+        pytest.skip('tcgen05 path: head_dim 64 only')
 
 
 def assert_close(got, ref, tol, what=''):
@@ -208,8 +209,8 @@ def test_invalid_arguments_are_rejected():
 
 
 def test_forcing_tcgen05_on_unsupported_input_is_an_error():
-    q = torch.randn(2, 64, 128, device=DEV)
-    k = torch.randn(2, 77, 128, device=DEV)
+    q = torch.randn(2, 64, 80, device=DEV)       # head_dim 40
+    k = torch.randn(2, 77, 80, device=DEV)
     with pytest.raises(_native.NativeError) as e:
         ops.accumulate_layer(q, k, 2, flags=_native.ACC_FORCE_MMA)
     assert e.value.code == _native.E_UNSUPPORTED
@@ -280,3 +281,20 @@ def test_materialised_probs_match_get_attention_scores(hw, heads, d, dtype, tol)
     from oracle import daam_oracle as O
     want = 2 * O.port_unravel(probs.float().cpu()).reshape(heads, 77, hw)
     assert rel_err(acc[0], want) < 1e-6
+
+
+def test_fp32_split_path_accuracy_and_properties():
+    """fp32 projections on tensor cores (three bf16 terms per value, six products): as accurate as the fp32 SIMT kernel
+    (both within 1e-5 of the oracle), including peaky logits, partial tiles and several layers per launch."""
+    g = torch.Generator().manual_seed(77)
+    for hw, heads, gain in [(4096, 5, 1.0), (1024, 10, 3.0), (576, 3, 1.0), (16, 2, 6.0)]:
+        q = (torch.randn(2, hw, heads * 64, generator=g) * gain).to(DEV)
+        k = torch.randn(2, 77, heads * 64, generator=g).to(DEV)
+        ref = oracle_layer_maps(q, k, heads, 0.125).unsqueeze(0)
+        split = ops.accumulate_layer(q, k, heads, flags=_native.ACC_FORCE_MMA)
+        simt = ops.accumulate_layer(q, k, heads, flags=_native.ACC_FORCE_SIMT)
+        torch.cuda.synchronize()
+        e_split, e_simt = rel_err(split, ref), rel_err(simt, ref)
+        assert e_split < 1e-5 and e_simt < 1e-5, (hw, heads, e_split, e_simt)
+        sums = split.double().sum(dim=(2, 3))
+        assert torch.allclose(sums, torch.full_like(sums, float(hw)), rtol=1e-6)

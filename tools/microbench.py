@@ -43,7 +43,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--workload', default='sd21')
     ap.add_argument('--prompts', type=int, nargs='+', default=[1, 8])
-    ap.add_argument('--dtypes', nargs='+', default=['bf16', 'fp32'])
+    ap.add_argument('--dtypes', nargs='+', default=['bf16', 'fp32'])   # fp32: mma-* = split (3 x bf16) form
     ap.add_argument('--variants', nargs='+', default=None)
     args = ap.parse_args()
     peak, _ = measured_peak()
