@@ -46,7 +46,7 @@ constexpr int kThreads = 192;
 constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kPBytes + 128;
 // split (fp32) form: a stage holds Q1 Q2 Q3 K1 K2 K3; warps 6-9 convert; one CTA per SM
 constexpr int kSplitStageBytes = 3 * kStageBytes;
-constexpr int kSplitThreads = 320;
+constexpr int kSplitThreads = 448;                 // + two converter groups of 4 warps, one per stage
 constexpr int kSplitSmemBytes = 1024 + kStages * kSplitStageBytes + kPBytes + 128;
 
 struct MmaParams {
@@ -267,12 +267,14 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
 
   if (kSplit && warp >= 6) {
     // ===== converter warps (fp32 projections): global fp32 -> three bf16 operand tiles per operand =====
-    const int ctid = threadIdx.x - 192;
+    // group g (warps 6-9 / 10-13) fills stage g with tiles g, g + 2, ...: two tiles' loads and conversions overlap
+    const int group = (warp - 6) >> 2;
+    const int ctid = (threadIdx.x - 192) & 127;
     int li = 0;
-    for (int i = 0; i < count; ++i) {
+    for (int i = group; i < count; i += kStages) {
       const Tile t = decode_tile(P, first + i, li);
       const LayerParams& L = P.layer[t.li];
-      const int s = i % kStages;
+      const int s = group;
       const uint32_t ph = (uint32_t)(i / kStages) & 1u;
       mbar_wait(empty0 + 8 * s, ph ^ 1u);
       uint8_t* stage = gen + s * kStageBytesT;
