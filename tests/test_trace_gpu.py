@@ -240,3 +240,32 @@ def test_per_head_heat_maps_equal_the_all_heads_sweep():
                 assert rel_err(single, m) < 1e-6, (factor, layer, head)
         keys2, _ = tc.compute_per_head_heat_maps(factors=[2])
         assert {k[0] for k in keys2} == {2}
+
+
+def test_collection_interface_update_and_to_experiment(tmp_path):
+    """RawHeatMapCollection keeps the reference's interface (heatmap.py:148-172) on top of the slabs, and to_experiment
+    (trace.py:68-81) packages the last generation."""
+    from daam_b200 import GenerationExperiment, RawHeatMapCollection
+    coll = RawHeatMapCollection()
+    a, b = torch.rand(77, 16, 16, device=DEV), torch.rand(77, 16, 16, device=DEV)
+    coll.update(4, 2, 0, a)
+    coll.update(4, 2, 1, b)
+    coll.update(4, 2, 0, b)
+    coll.update(1, 5, 0, torch.ones(77, 64, 64, device=DEV))
+    got = dict(coll)
+    assert set(got) == {(4, 2, 0), (4, 2, 1), (1, 5, 0)}
+    assert torch.allclose(got[(4, 2, 0)], a + b) and torch.allclose(got[(4, 2, 1)], b)
+    assert coll.factors() == {1, 4} and coll.layers() == {2, 5} and coll.heads() == {0, 1} and len(coll) == 3
+    coll.clear()
+    assert len(coll) == 0 and list(coll) == []
+
+    pipe = make_pipeline(TINY_SPEC, dtype=torch.float16, device=DEV, seed=8)
+    with trace(pipe) as tc:
+        pipe(PROMPT, num_inference_steps=1, generator=torch.Generator().manual_seed(1))
+        exp = tc.to_experiment(str(tmp_path), seed=1, id='gen0', normalize=True)
+        ref = tc.compute_global_heat_map(normalize=True).heat_maps
+    assert isinstance(exp, GenerationExperiment) and exp.prompt == PROMPT and torch.equal(exp.global_heat_map, ref)
+    exp.tokenizer = None          # the synthetic tokenizer is a local class; real ones pickle
+    exp.save()
+    back = GenerationExperiment.load(tmp_path / 'gen0', map_location='cpu')
+    assert torch.equal(back.global_heat_map, ref.cpu()) and back.seed == 1
