@@ -460,6 +460,7 @@ def main():
     ap.add_argument('--dtype', default=None, choices=['bf16', 'fp16', 'fp32'])
     ap.add_argument('--skip-overhead', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-eager', action='store_true', help='skip the eager (no CUDA graph) e2e leg')
     args = ap.parse_args()
     if args.dtype is None:
         args.dtype = 'bf16' if args.workload == 'sd21' else 'fp16'
@@ -483,7 +484,7 @@ def main():
     with torch.no_grad():
         ms, launches, n_sets = leg_value(args, layers, dtype, D, windows)
         e2e_ms, h2d, d2h = leg_e2e(args, spec, dtype, D, windows, cuda_graph=True)
-        eager_ms, _, _ = leg_e2e(args, spec, dtype, D, windows, cuda_graph=False)
+        eager_ms = leg_e2e(args, spec, dtype, D, windows, cuda_graph=False)[0] if not args.skip_eager else float('nan')
         overhead = None
         if not args.skip_overhead and D.rank == 0 and D.world == 1:
             try:
@@ -519,7 +520,8 @@ def main():
         'clocks': clocks,
         'e2e': {'value': px * args.steps * n / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps,
-                'eager_value': px * args.steps * n / (eager_ms * 1e-3), 'eager_ms_per_step': eager_ms / args.steps,
+                'eager_value': None if args.skip_eager else px * args.steps * n / (eager_ms * 1e-3),
+                'eager_ms_per_step': None if args.skip_eager else eager_ms / args.steps,
                 'what': 'with trace(pipe): pipe(prompt, K steps) on the cross-attn skeleton UNet (to_q/to_k/to_v, SDPA, '
                         'to_out + fused heat-map kernel), pinned-host inputs H2D every step, + compute_global_heat_map '
                         '(+ all_gather when N>1) + D2H of the maps; the pipeline replays the step from a CUDA graph '
