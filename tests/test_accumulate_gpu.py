@@ -298,3 +298,18 @@ def test_fp32_split_path_accuracy_and_properties():
         assert e_split < 1e-5 and e_simt < 1e-5, (hw, heads, e_split, e_simt)
         sums = split.double().sum(dim=(2, 3))
         assert torch.allclose(sums, torch.full_like(sums, float(hw)), rtol=1e-6)
+
+
+def test_empty_call_and_smallest_maps():
+    """Zero layers is a no-op; the smallest map the API admits (2x2 pixels) still goes through both kernels."""
+    before = _native.launch_count()
+    ops.accumulate([], DEV)
+    assert _native.launch_count() == before
+    g = torch.Generator().manual_seed(0)
+    for dtype, flags in [(torch.float16, _native.ACC_FORCE_MMA), (torch.float32, _native.ACC_FORCE_MMA),
+                         (torch.float32, _native.ACC_FORCE_SIMT)]:
+        q = torch.randn(2, 4, 64, generator=g).to(dtype).to(DEV)
+        k = torch.randn(2, 77, 64, generator=g).to(dtype).to(DEV)
+        acc = ops.accumulate_layer(q, k, 1, flags=flags)
+        torch.cuda.synchronize()
+        assert_close(acc[0], oracle_layer_maps(q, k, 1, 0.125), TOL[dtype], f'{dtype}')

@@ -143,3 +143,18 @@ def test_fast_and_generic_finalize_agree(monkeypatch, x, sides):
             keys = [k[h].cpu().numpy() for k in keep for h in (range(k.shape[0]) if head_sel < 0 else [head_sel])]
             ref = O.math_global_heat_map(keys, x, 23, normalize)
             assert rel_err(fast, ref) < 1e-5
+
+
+@pytest.mark.parametrize('n_rows', [1, 2, 3])
+def test_short_prompts_and_degenerate_normalisation(n_rows):
+    """rows[:n] with n = 1, 2: `maps[1:-1]` is empty, the reference divides by 1e-6 (trace.py:129-130); n = 3: one row."""
+    g = torch.Generator().manual_seed(n_rows)
+    key = torch.rand(2, 77, 32, 32, generator=g)
+    kd = key.to(DEV)
+    grp = [_native.DaamKeyGroup(acc=kd.data_ptr(), heads=2, h=32, w=32, tokens=77, head_sel=-1, reserved=0)]
+    store = [((2, 0, h), key[h]) for h in range(2)]
+    for normalize in (False, True):
+        out = run_finalize(grp, n_rows, normalize)
+        ref = O.port_global_heat_map(store, 4096, n_rows - 2, normalize=normalize)
+        assert out.shape == ref.shape == (n_rows, 64, 64)
+        assert rel_err(out, ref) < 1e-5
