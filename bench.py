@@ -528,7 +528,8 @@ def main():
                         '(eager_*: same without graph replay, host-launch bound)'},
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': recorded_traffic(args.workload), 'kernel': 'daam accumulate (softmax(QK^T)->unravel->+=)',
+                     'traffic': recorded_traffic(args.workload) if args.dtype == 'bf16' and args.prompts == 1 else None,
+                     'kernel': 'daam accumulate (softmax(QK^T)->unravel->+=)',
                      'algorithmic_bytes_per_launch': bytes_step, 'peak_source': peak_src},
         'cpu_baseline': cpu,
         'hook_overhead': overhead,
