@@ -523,7 +523,8 @@ int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStre
     }
     if (int rc = make_acc_map(L.acc, L.hw, L.n_prompts * L.heads * kTokens, &mp.amap[i])) return rc;
   }
-  static bool configured = false;
+  static bool configured_dev[64] = {};                // the attribute is per device
+  bool& configured = configured_dev[dev.device & 63];
   if (!configured) {
     DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmemBytes));

@@ -61,7 +61,8 @@ int launch_accumulate_simt(const LaunchParams& p, const DeviceInfo& dev, cudaStr
   int dmax = 0;
   for (int i = 0; i < p.n_layers; ++i) dmax = p.layer[i].head_dim > dmax ? p.layer[i].head_dim : dmax;
   const size_t smem = sizeof(float) * simt::tile_smem_floats(dmax);
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {};              // the attribute is per device
+  size_t& configured = configured_dev[dev.device & 63];
   if (smem > configured) {
     DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));

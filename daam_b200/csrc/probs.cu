@@ -111,7 +111,8 @@ extern "C" int daam_attention_probs(const daam_layer* layer, void* probs, void* 
   const size_t need = (size_t)p.layer[0].head_dim * kTokensPad + (size_t)kTilePixels * kTokens;   // K^T + staged P
   if (need > floats) floats = need;
   const size_t smem = floats * sizeof(float);
-  static size_t configured = 0;
+  static size_t configured_dev[64] = {};              // the attribute is per device
+  size_t& configured = configured_dev[dev.device & 63];
   if (smem > configured) {
     DAAM_CUDA_TRY(cudaFuncSetAttribute(attention_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

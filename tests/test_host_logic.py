@@ -187,3 +187,17 @@ def test_generation_experiment_roundtrip_and_reference_dump(tmp_path):
             del sys.modules['daam']
     ref = GenerationExperiment.load(tmp_path / 'ref')
     assert isinstance(ref, GenerationExperiment) and ref.prompt == 'ref prompt' and torch.equal(ref.global_heat_map, maps)
+
+
+def test_bench_workload_definitions_match_the_survey():
+    """13.80 Mpx and 135.1 MB of algorithmic traffic per SD-2.1 step (bf16), 15 / 60 traced layers."""
+    import bench
+    sd21, sdxl = bench.traced_layers('sd21'), bench.traced_layers('sdxl')
+    assert len(sd21) == 15 and len(sdxl) == 60
+    assert bench.px_per_step(sd21) == 13_798_400
+    assert bench.literal_px_per_step(sd21) == 15 * 77 * 4096
+    assert abs(bench.algorithmic_bytes_per_step(sd21, esize=2) / 1e6 - 135.05) < 0.01
+    assert abs(bench.algorithmic_bytes_per_step(sd21, esize=4) / 1e6 - 159.71) < 0.01
+    # SDXL default trace: 10 layers at 64^2 with 10 heads (30.57 MB each), 50 at 32^2 with 20 heads (15.43 MB each)
+    assert abs(bench.algorithmic_bytes_per_step(sdxl, esize=2) / 1e6 - (10 * 30.57 + 50 * 15.43)) < 0.5
+    assert bench.px_per_step(sd21, n_prompts=8) == 8 * 13_798_400
