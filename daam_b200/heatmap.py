@@ -206,13 +206,9 @@ class WordHeatMap:
             plt.savefig(out_file)
 
     def compute_ioa(self, other: 'WordHeatMap') -> float:
-        """Intersection over own area of two (binarised) maps of equal size -- daam/evaluate.py:26-35 without its
-        resize branch (the word maps of one GlobalHeatMap always share a size)."""
-        a, b = self.heatmap, other.heatmap
-        if a.shape != b.shape:
-            raise ValueError('compute_ioa expects maps of equal size')
-        inter = (a * b).sum()
-        return (inter / (a.sum() + 1e-8)).item()
+        """Intersection over own area -- daam/evaluate.py:26-35 (heatmap.py:95-96)."""
+        from .evaluate import compute_ioa
+        return compute_ioa(self.heatmap, other.heatmap)
 
 
 class GlobalHeatMap:

@@ -158,3 +158,22 @@ def test_short_prompts_and_degenerate_normalisation(n_rows):
         ref = O.port_global_heat_map(store, 4096, n_rows - 2, normalize=normalize)
         assert out.shape == ref.shape == (n_rows, 64, 64)
         assert rel_err(out, ref) < 1e-5
+
+
+def test_iou_ioa_match_the_reference_formulas():
+    """daam/evaluate.py:14-35, including the resize-and-binarise branch when the masks differ in size."""
+    import torch.nn.functional as F
+    from daam_b200 import compute_ioa, compute_iou
+    g = torch.Generator().manual_seed(5)
+    a = (torch.rand(64, 64, generator=g) > 0.5).float()
+    b = (torch.rand(64, 64, generator=g) > 0.5).float()
+    inter = (a * b).sum()
+    assert compute_iou(a.to(DEV), b.to(DEV)) == pytest.approx((inter / (a.sum() + b.sum() - inter + 1e-8)).item(), rel=1e-6)
+    assert compute_ioa(a.to(DEV), b.to(DEV)) == pytest.approx((inter / (a.sum() + 1e-8)).item(), rel=1e-6)
+    small = torch.rand(16, 16, generator=g) * 2.0
+    big = (torch.rand(64, 64, generator=g) > 0.5).float()
+    up = F.interpolate(small[None, None], size=(64, 64), mode='bicubic').squeeze()
+    up = (up >= 1).float()
+    i2 = (up * big).sum()
+    assert compute_iou(small.to(DEV), big.to(DEV)) == pytest.approx((i2 / (up.sum() + big.sum() - i2 + 1e-8)).item(), rel=2e-3)
+    assert compute_ioa(small.to(DEV), big.to(DEV)) == pytest.approx((i2 / (up.sum() + 1e-8)).item(), rel=2e-3)
