@@ -1,4 +1,4 @@
-// Fused softmax(QK^T) -> unravel -> accumulate, tcgen05 / TMA / TMEM variant for 16-bit projections (head_dim 64).
+// Fused softmax(QK^T) -> unravel -> accumulate, tcgen05 / TMA / TMEM variant (head_dim up to 192 in 64-wide K chunks).
 //
 // One tile = 128 pixels x 77 tokens of one (layer, prompt, head). Per tile:
 //   TMA        Q tile [128 x 64] and K [77(+3 zero rows) x 64] -> shared memory, 128B-swizzled K-major (the UMMA
@@ -22,6 +22,10 @@
 // (x = x1 + x2 + x3 carries all 24 significand bits), store them as three swizzled operand tiles each, and the MMA
 // warp accumulates the six products of order <= 2^-16 (q1k1 + q1k2 + q2k1 + q1k3 + q2k2 + q3k1) in fp32 in TMEM:
 // 24 MMAs per tile instead of 4, still far from the tensor pipe's limit, and the path stays HBM-bound.
+//
+// head_dim other than 64 (SD-1.x: 40 / 80 / 160): the contraction runs in 64-wide K chunks, one chunk per smem stage,
+// accumulated into the same TMEM accumulator; the last chunk is zero-filled beyond head_dim (by the TMA unit, or by the
+// converter warps) and issues only the MMAs that cover live columns.
 //
 // Replaces daam/trace.py:276 (get_attention_scores), :219-244 (_unravel_attn) and :293-294 (update loop).
 #include <cuda.h>
@@ -186,16 +190,16 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& p1, uint4& p2
 }
 
 // Converter warps (split form): rows [row0, row0 + n_rows_live) of a fp32 [rows x 64] operand -> three 128B-swizzled
-// K-major bf16 tiles at dst, dst + part_bytes, dst + 2 * part_bytes. `n_chunks` 16-byte chunks (8 floats) in total,
-// chunk = row * 8 + group; rows >= n_rows_live are written as zeros. ctid: 0..127.
+// K-major bf16 tiles at dst, dst + part_bytes, dst + 2 * part_bytes. 16-byte chunks of 8 floats, chunk = row * 8 +
+// group; rows >= n_rows_live and columns >= n_cols_live (a multiple of 8) are written as zeros. ctid: 0..127.
 template <int kChunksPerThread>
 __device__ __forceinline__ void convert_operand(const float* src_base, long long row_stride, int n_rows_live,
-                                                uint8_t* dst, int part_bytes, int ctid) {
+                                                int n_cols_live, uint8_t* dst, int part_bytes, int ctid) {
   float4 lo[kChunksPerThread], hi[kChunksPerThread];
 #pragma unroll
   for (int c = 0; c < kChunksPerThread; ++c) {            // all loads first: 2 x kChunksPerThread in flight per thread
     const int chunk = ctid + 128 * c, r = chunk >> 3, g = chunk & 7;
-    if (r < n_rows_live) {
+    if (r < n_rows_live && g * 8 < n_cols_live) {
       const float4* srcp = reinterpret_cast<const float4*>(src_base + (long long)r * row_stride + g * 8);
       lo[c] = __ldg(srcp);
       hi[c] = __ldg(srcp + 1);
@@ -267,72 +271,85 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
 
   if (kSplit && warp >= 6) {
     // ===== converter warps (fp32 projections): global fp32 -> three bf16 operand tiles per operand =====
-    // group g (warps 6-9 / 10-13) fills stage g with tiles g, g + 2, ...: two tiles' loads and conversions overlap
+    // group g (warps 6-9 / 10-13) fills stage g with the load iterations j = g, g + 2, ... (one iteration = one 64-wide
+    // K chunk of one tile): two iterations' loads and conversions overlap
     const int group = (warp - 6) >> 2;
     const int ctid = (threadIdx.x - 192) & 127;
-    int li = 0;
-    for (int i = group; i < count; i += kStages) {
+    int li = 0, j = 0;
+    for (int i = 0; i < count; ++i) {
       const Tile t = decode_tile(P, first + i, li);
       const LayerParams& L = P.layer[t.li];
-      const int s = group;
-      const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-      mbar_wait(empty0 + 8 * s, ph ^ 1u);
-      uint8_t* stage = gen + s * kStageBytesT;
-      const float* qsrc = static_cast<const float*>(L.q) + t.prompt * L.qs_prompt + t.head * L.qs_head +
-                          (long long)t.pixel0 * L.qs_pixel;
-      const float* ksrc = static_cast<const float*>(L.k) + t.prompt * L.ks_prompt + t.head * L.ks_head;
-      convert_operand<8>(qsrc, L.qs_pixel, min(kTilePixels, L.hw - t.pixel0), stage, kQBytes, ctid);
-      convert_operand<5>(ksrc, L.ks_token, kTokens, stage + 3 * kQBytes, kKBytes, ctid);
-      fence_proxy_async();                             // generic-proxy stores -> visible to the tensor core's reads
-      mbar_arrive(full0 + 8 * s);
+      const int n_chunks = (L.head_dim + 63) >> 6;
+      for (int c = 0; c < n_chunks; ++c, ++j) {
+        if ((j & 1) != group) continue;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        mbar_wait(empty0 + 8 * group, ph ^ 1u);
+        uint8_t* stage = gen + group * kStageBytesT;
+        const int cols = min(64, L.head_dim - 64 * c);
+        const float* qsrc = static_cast<const float*>(L.q) + t.prompt * L.qs_prompt + t.head * L.qs_head +
+                            (long long)t.pixel0 * L.qs_pixel + 64 * c;
+        const float* ksrc = static_cast<const float*>(L.k) + t.prompt * L.ks_prompt + t.head * L.ks_head + 64 * c;
+        convert_operand<8>(qsrc, L.qs_pixel, min(kTilePixels, L.hw - t.pixel0), cols, stage, kQBytes, ctid);
+        convert_operand<5>(ksrc, L.ks_token, kTokens, cols, stage + 3 * kQBytes, kKBytes, ctid);
+        fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core's reads
+        mbar_arrive(full0 + 8 * group);
+      }
     }
   } else if (warp == 4) {
     // ===== TMA producer (16-bit projections) =====
     if (!kSplit && lane == 0) {
-      int li = 0;
+      int li = 0, j = 0;
       for (int i = 0; i < count; ++i) {
         const Tile t = decode_tile(P, first + i, li);
-        const int s = i % kStages;
-        const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-        mbar_wait(empty0 + 8 * s, ph ^ 1u);
-        mbar_expect_tx(full0 + 8 * s, kStageBytes);
-        const uint32_t q_dst = base + s * kStageBytesT, k_dst = q_dst + kQBytes;
-        tma_load_4d(&MP.qmap[t.li], full0 + 8 * s, q_dst, 0, t.head, t.pixel0, t.prompt);
-        tma_load_4d(&MP.kmap[t.li], full0 + 8 * s, k_dst, 0, t.head, 0, t.prompt);
+        const int n_chunks = (P.layer[t.li].head_dim + 63) >> 6;
+        for (int c = 0; c < n_chunks; ++c, ++j) {      // one load iteration = one 64-wide K chunk of one tile
+          const int s = j % kStages;
+          const uint32_t ph = (uint32_t)(j / kStages) & 1u;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          mbar_expect_tx(full0 + 8 * s, kStageBytes);
+          const uint32_t q_dst = base + s * kStageBytesT, k_dst = q_dst + kQBytes;
+          tma_load_4d(&MP.qmap[t.li], full0 + 8 * s, q_dst, 64 * c, t.head, t.pixel0, t.prompt);
+          tma_load_4d(&MP.kmap[t.li], full0 + 8 * s, k_dst, 64 * c, t.head, 0, t.prompt);
+        }
       }
     }
   } else if (warp == 5) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      int li = 0;
+      int li = 0, j = 0;
       for (int i = 0; i < count; ++i) {
         const Tile t = decode_tile(P, first + i, li);
-        const int s = i % kStages, a = i & 1;
-        const uint32_t ph = (uint32_t)(i / kStages) & 1u, aph = (uint32_t)(i >> 1) & 1u;
-        mbar_wait(tempty0 + 8 * a, aph ^ 1u);          // epilogue has drained this accumulator
-        mbar_wait(full0 + 8 * s, ph);                  // TMA bytes have landed
-        tc_fence_after();
-        const uint32_t q_src = base + s * kStageBytesT;
+        const LayerParams& L = P.layer[t.li];
+        const int a = i & 1;
+        const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+        const int n_chunks = (L.head_dim + 63) >> 6;
         const uint32_t d_tmem = tmem_base + a * kAccCols;
-        if constexpr (kSplit) {
-          // q.k = sum of the six split products up to order 2^-16, smallest first; every operand is bf16
-          const uint32_t k_src = q_src + 3 * kQBytes;
-          const uint32_t idesc = umma_idesc(true);
-          constexpr int qa[6] = {2, 0, 1, 1, 0, 0}, kb[6] = {0, 2, 1, 0, 1, 0};
+        mbar_wait(tempty0 + 8 * a, aph ^ 1u);          // epilogue has drained this accumulator
+        for (int c = 0; c < n_chunks; ++c, ++j) {
+          const int s = j % kStages;
+          const uint32_t ph = (uint32_t)(j / kStages) & 1u;
+          mbar_wait(full0 + 8 * s, ph);                // the chunk's operand tiles have landed
+          tc_fence_after();
+          const uint32_t q_src = base + s * kStageBytesT;
+          const int k_steps = (min(64, L.head_dim - 64 * c) + 15) >> 4;   // UMMA_K 16 = 32 bytes along the swizzled row
+          if constexpr (kSplit) {
+            // q.k = sum of the six split products up to order 2^-16, smallest first; every operand is bf16
+            const uint32_t k_src = q_src + 3 * kQBytes;
+            const uint32_t idesc = umma_idesc(true);
+            constexpr int qa[6] = {2, 0, 1, 1, 0, 0}, kb[6] = {0, 2, 1, 0, 1, 0};
 #pragma unroll
-          for (int p = 0; p < 6; ++p)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(d_tmem, umma_desc_sw128(q_src + qa[p] * kQBytes + 32 * k),
-                       umma_desc_sw128(k_src + kb[p] * kKBytes + 32 * k), idesc, (p | k) != 0);
-        } else {
-          const uint32_t k_src = q_src + kQBytes;
-          const uint32_t idesc = umma_idesc(P.layer[t.li].dtype == DAAM_BF16);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)                  // head_dim 64 = 4 x UMMA_K 16 (32 bytes along the swizzled row)
-            umma_f16(d_tmem, umma_desc_sw128(q_src + 32 * k), umma_desc_sw128(k_src + 32 * k), idesc, k > 0);
+            for (int p = 0; p < 6; ++p)
+              for (int k = 0; k < k_steps; ++k)
+                umma_f16(d_tmem, umma_desc_sw128(q_src + qa[p] * kQBytes + 32 * k),
+                         umma_desc_sw128(k_src + kb[p] * kKBytes + 32 * k), idesc, (c | p | k) != 0);
+          } else {
+            const uint32_t k_src = q_src + kQBytes;
+            const uint32_t idesc = umma_idesc(L.dtype == DAAM_BF16);
+            for (int k = 0; k < k_steps; ++k)
+              umma_f16(d_tmem, umma_desc_sw128(q_src + 32 * k), umma_desc_sw128(k_src + 32 * k), idesc, (c | k) != 0);
+          }
+          umma_commit(empty0 + 8 * s);                 // frees the smem stage once the MMAs have read it
         }
-        umma_commit(empty0 + 8 * s);                   // frees the smem stage once the MMAs have read it
         umma_commit(tfull0 + 8 * a);                   // accumulator ready for the epilogue
       }
     }
@@ -453,10 +470,11 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash>& map_cache() {
 }
 std::mutex g_map_mu;
 
-// {dim 64, heads, rows, prompts} view of a projection; box = one head's [box_rows x 64] tile, 128B-swizzled.
-int make_qk_map(const void* ptr, int dtype, int heads, int rows, int prompts, long long s_head, long long s_row,
-                long long s_prompt, int box_rows, CUtensorMap* out) {
-  MapKey key{ptr, s_head, s_row, s_prompt, heads, rows, prompts * 1024 + box_rows, dtype << 4};
+// {head_dim, heads, rows, prompts} view of a projection; box = [box_rows x 64 dims] of one head, 128B-swizzled (columns
+// beyond head_dim in the last K chunk are zero-filled).
+int make_qk_map(const void* ptr, int dtype, int head_dim, int heads, int rows, int prompts, long long s_head,
+                long long s_row, long long s_prompt, int box_rows, CUtensorMap* out) {
+  MapKey key{ptr, s_head, s_row, s_prompt, heads, rows, prompts * 1024 + box_rows, (dtype << 4) | (head_dim << 8)};
   {
     std::lock_guard<std::mutex> lock(g_map_mu);
     auto it = map_cache().find(key);
@@ -464,7 +482,7 @@ int make_qk_map(const void* ptr, int dtype, int heads, int rows, int prompts, lo
   }
   EncodeFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DAAM_E_CUDA; }
-  const cuuint64_t dims[4] = {64, (cuuint64_t)heads, (cuuint64_t)rows, (cuuint64_t)prompts};
+  const cuuint64_t dims[4] = {(cuuint64_t)head_dim, (cuuint64_t)heads, (cuuint64_t)rows, (cuuint64_t)prompts};
   auto bytes = [](long long s) { return (cuuint64_t)(s > 0 ? s : 8) * 2; };
   const cuuint64_t strides[3] = {bytes(s_head), bytes(s_row), bytes(s_prompt)};
   const cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
@@ -506,7 +524,8 @@ int make_acc_map(float* acc, int hw, int rows, CUtensorMap* out) {
 }  // namespace
 
 bool mma_supported(const LayerParams& L) {
-  return L.head_dim == 64 && L.vec_ok && L.qs_head > 0 && L.qs_pixel > 0 && L.ks_head > 0 && L.ks_token > 0;
+  return L.head_dim % 8 == 0 && L.head_dim <= 192 && L.vec_ok && L.qs_head > 0 && L.qs_pixel > 0 && L.ks_head > 0 &&
+         L.ks_token > 0;
 }
 
 int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStream_t stream) {
@@ -518,8 +537,8 @@ int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStre
     const LayerParams& L = p.layer[i];
     if ((L.dtype == DAAM_F32) != split) { set_error("mixed fp32 / 16-bit layers in one tcgen05 pack"); return DAAM_E_INVALID; }
     if (!split) {
-      if (int rc = make_qk_map(L.q, L.dtype, L.heads, L.hw, L.n_prompts, L.qs_head, L.qs_pixel, L.qs_prompt, kTilePixels, &mp.qmap[i])) return rc;
-      if (int rc = make_qk_map(L.k, L.dtype, L.heads, kTokens, L.n_prompts, L.ks_head, L.ks_token, L.ks_prompt, kTokensPad, &mp.kmap[i])) return rc;
+      if (int rc = make_qk_map(L.q, L.dtype, L.head_dim, L.heads, L.hw, L.n_prompts, L.qs_head, L.qs_pixel, L.qs_prompt, kTilePixels, &mp.qmap[i])) return rc;
+      if (int rc = make_qk_map(L.k, L.dtype, L.head_dim, L.heads, kTokens, L.n_prompts, L.ks_head, L.ks_token, L.ks_prompt, kTokensPad, &mp.kmap[i])) return rc;
     }
     if (int rc = make_acc_map(L.acc, L.hw, L.n_prompts * L.heads * kTokens, &mp.amap[i])) return rc;
   }

@@ -26,10 +26,10 @@ PATHS = [
 
 
 def skip_unless_mma_applies(path, dtype, head_dim):
-    """The tcgen05 kernel takes head_dim 64 (16-bit operands directly, fp32 as three bf16 terms); forcing it elsewhere
-    is an error by design."""
-    if path.startswith('mma') and head_dim != 64:
-        pytest.skip('tcgen05 path: head_dim 64 only')
+    """The tcgen05 kernel takes every head_dim that is a multiple of 8 up to 192 (16-bit operands directly, fp32 as three
+    bf16 terms, 64-wide K chunks); forcing it elsewhere is an error by design."""
+    if path.startswith('mma') and (head_dim % 8 != 0 or head_dim > 192):
+        pytest.skip('tcgen05 path: head_dim multiple of 8, <= 192')
 
 
 def assert_close(got, ref, tol, what=''):
@@ -209,11 +209,15 @@ def test_invalid_arguments_are_rejected():
 
 
 def test_forcing_tcgen05_on_unsupported_input_is_an_error():
-    q = torch.randn(2, 64, 80, device=DEV)       # head_dim 40
-    k = torch.randn(2, 77, 80, device=DEV)
+    wide_q = torch.randn(2, 64, 136, device=DEV)
+    wide_k = torch.randn(2, 77, 136, device=DEV)
+    q, k = wide_q[:, :, 3:131], wide_k[:, :, 3:131]          # rows not 16-byte aligned: no TMA / vector loads
     with pytest.raises(_native.NativeError) as e:
         ops.accumulate_layer(q, k, 2, flags=_native.ACC_FORCE_MMA)
     assert e.value.code == _native.E_UNSUPPORTED
+    acc = ops.accumulate_layer(q, k, 2)                       # AUTO falls back to the SIMT kernel
+    torch.cuda.synchronize()
+    assert_close(acc[0], oracle_layer_maps(q.contiguous(), k.contiguous(), 2, 0.125), 1e-5)
 
 
 @pytest.mark.parametrize('mode', [_native.ACC_RMW_RED, _native.ACC_RMW_LDST])
@@ -313,3 +317,18 @@ def test_empty_call_and_smallest_maps():
         acc = ops.accumulate_layer(q, k, 1, flags=flags)
         torch.cuda.synchronize()
         assert_close(acc[0], oracle_layer_maps(q, k, 1, 0.125), TOL[dtype], f'{dtype}')
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize('hw,heads,d', [(4096, 8, 40), (1024, 8, 80), (256, 8, 160), (64, 4, 192), (1024, 4, 8)])
+def test_sd1x_head_dims_on_tensor_cores(hw, heads, d, dtype):
+    """SD-1.x head dims (40 / 80 / 160) and other multiples of 8: K-chunked tcgen05 path == SIMT path == oracle."""
+    g = torch.Generator().manual_seed(d * 7 + hw)
+    q = torch.randn(2, hw, heads * d, generator=g).to(dtype).to(DEV)
+    k = torch.randn(2, 77, heads * d, generator=g).to(dtype).to(DEV)
+    mma = ops.accumulate_layer(q, k, heads, flags=_native.ACC_FORCE_MMA)
+    simt = ops.accumulate_layer(q, k, heads, flags=_native.ACC_FORCE_SIMT)
+    torch.cuda.synchronize()
+    ref = oracle_layer_maps(q, k, heads, d ** -0.5).unsqueeze(0)
+    assert_close(mma, ref, TOL[dtype], f'mma d{d}')
+    assert_close(simt, ref, TOL[dtype], f'simt d{d}')
