@@ -339,14 +339,18 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
             constexpr int qa[6] = {2, 0, 1, 1, 0, 0}, kb[6] = {0, 2, 1, 0, 1, 0};
 #pragma unroll
             for (int p = 0; p < 6; ++p)
-              for (int k = 0; k < k_steps; ++k)
-                umma_f16(d_tmem, umma_desc_sw128(q_src + qa[p] * kQBytes + 32 * k),
-                         umma_desc_sw128(k_src + kb[p] * kKBytes + 32 * k), idesc, (c | p | k) != 0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < k_steps)
+                  umma_f16(d_tmem, umma_desc_sw128(q_src + qa[p] * kQBytes + 32 * k),
+                           umma_desc_sw128(k_src + kb[p] * kKBytes + 32 * k), idesc, (c | p | k) != 0);
           } else {
             const uint32_t k_src = q_src + kQBytes;
             const uint32_t idesc = umma_idesc(L.dtype == DAAM_BF16);
-            for (int k = 0; k < k_steps; ++k)
-              umma_f16(d_tmem, umma_desc_sw128(q_src + 32 * k), umma_desc_sw128(k_src + 32 * k), idesc, (c | k) != 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < k_steps)
+                umma_f16(d_tmem, umma_desc_sw128(q_src + 32 * k), umma_desc_sw128(k_src + 32 * k), idesc, (c | k) != 0);
           }
           umma_commit(empty0 + 8 * s);                 // frees the smem stage once the MMAs have read it
         }
