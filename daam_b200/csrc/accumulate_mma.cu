@@ -220,7 +220,9 @@ __device__ __forceinline__ void convert_operand(const float* src_base, long long
   }
 }
 
-template <bool kSplit>
+// kChunked: some layer of the launch has head_dim > 64 (several K chunks per tile); the common single-chunk case keeps
+// its simpler loops (one load iteration per tile).
+template <bool kSplit, bool kChunked>
 __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, kSplit ? 1 : 2)
 accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
   constexpr int kStageBytesT = kSplit ? kSplitStageBytes : kStageBytes;
@@ -275,24 +277,32 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
     // K chunk of one tile): two iterations' loads and conversions overlap
     const int group = (warp - 6) >> 2;
     const int ctid = (threadIdx.x - 192) & 127;
-    int li = 0, j = 0;
-    for (int i = 0; i < count; ++i) {
-      const Tile t = decode_tile(P, first + i, li);
-      const LayerParams& L = P.layer[t.li];
-      const int n_chunks = (L.head_dim + 63) >> 6;
-      for (int c = 0; c < n_chunks; ++c, ++j) {
-        if ((j & 1) != group) continue;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-        mbar_wait(empty0 + 8 * group, ph ^ 1u);
-        uint8_t* stage = gen + group * kStageBytesT;
-        const int cols = min(64, L.head_dim - 64 * c);
-        const float* qsrc = static_cast<const float*>(L.q) + t.prompt * L.qs_prompt + t.head * L.qs_head +
-                            (long long)t.pixel0 * L.qs_pixel + 64 * c;
-        const float* ksrc = static_cast<const float*>(L.k) + t.prompt * L.ks_prompt + t.head * L.ks_head + 64 * c;
-        convert_operand<8>(qsrc, L.qs_pixel, min(kTilePixels, L.hw - t.pixel0), cols, stage, kQBytes, ctid);
-        convert_operand<5>(ksrc, L.ks_token, kTokens, cols, stage + 3 * kQBytes, kKBytes, ctid);
-        fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core's reads
-        mbar_arrive(full0 + 8 * group);
+    auto convert_chunk = [&](const Tile& t, const LayerParams& L, int c, uint32_t ph) {
+      mbar_wait(empty0 + 8 * group, ph ^ 1u);
+      uint8_t* stage = gen + group * kStageBytesT;
+      const int cols = min(64, L.head_dim - 64 * c);
+      const float* qsrc = static_cast<const float*>(L.q) + t.prompt * L.qs_prompt + t.head * L.qs_head +
+                          (long long)t.pixel0 * L.qs_pixel + 64 * c;
+      const float* ksrc = static_cast<const float*>(L.k) + t.prompt * L.ks_prompt + t.head * L.ks_head + 64 * c;
+      convert_operand<8>(qsrc, L.qs_pixel, min(kTilePixels, L.hw - t.pixel0), cols, stage, kQBytes, ctid);
+      convert_operand<5>(ksrc, L.ks_token, kTokens, cols, stage + 3 * kQBytes, kKBytes, ctid);
+      fence_proxy_async();                             // generic-proxy stores -> visible to the tensor core's reads
+      mbar_arrive(full0 + 8 * group);
+    };
+    int li = 0;
+    if constexpr (!kChunked) {
+      for (int i = group; i < count; i += kStages) {   // load iteration == tile
+        const Tile t = decode_tile(P, first + i, li);
+        convert_chunk(t, P.layer[t.li], 0, (uint32_t)(i >> 1) & 1u);
+      }
+    } else {
+      int j = 0;
+      for (int i = 0; i < count; ++i) {
+        const Tile t = decode_tile(P, first + i, li);
+        const LayerParams& L = P.layer[t.li];
+        const int n_chunks = (L.head_dim + 63) >> 6;
+        for (int c = 0; c < n_chunks; ++c, ++j)
+          if ((j & 1) == group) convert_chunk(t, L, c, (uint32_t)(j >> 1) & 1u);
       }
     }
   } else if (warp == 4) {
@@ -301,7 +311,7 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
       int li = 0, j = 0;
       for (int i = 0; i < count; ++i) {
         const Tile t = decode_tile(P, first + i, li);
-        const int n_chunks = (P.layer[t.li].head_dim + 63) >> 6;
+        const int n_chunks = kChunked ? (P.layer[t.li].head_dim + 63) >> 6 : 1;
         for (int c = 0; c < n_chunks; ++c, ++j) {      // one load iteration = one 64-wide K chunk of one tile
           const int s = j % kStages;
           const uint32_t ph = (uint32_t)(j / kStages) & 1u;
@@ -322,7 +332,7 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
         const LayerParams& L = P.layer[t.li];
         const int a = i & 1;
         const uint32_t aph = (uint32_t)(i >> 1) & 1u;
-        const int n_chunks = (L.head_dim + 63) >> 6;
+        const int n_chunks = kChunked ? (L.head_dim + 63) >> 6 : 1;
         const uint32_t d_tmem = tmem_base + a * kAccCols;
         mbar_wait(tempty0 + 8 * a, aph ^ 1u);          // epilogue has drained this accumulator
         for (int c = 0; c < n_chunks; ++c, ++j) {
@@ -549,8 +559,10 @@ int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStre
   static bool configured_dev[64] = {};                // the attribute is per device
   bool& configured = configured_dev[dev.device & 63];
   if (!configured) {
-    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmemBytes));
+    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmemBytes));
+    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmemBytes));
     configured = true;
   }
   int grid = dev.sm_count * (split ? 1 : 2);
@@ -568,8 +580,12 @@ int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStre
   attr[0].val.programmaticStreamSerializationAllowed = (p.pdl && capture == cudaStreamCaptureStatusNone) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (split) DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<true>, mp));
-  else DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<false>, mp));
+  bool chunked = false;
+  for (int i = 0; i < p.n_layers; ++i) chunked = chunked || p.layer[i].head_dim > 64;
+  if (split && chunked) DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<true, true>, mp));
+  else if (split) DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<true, false>, mp));
+  else if (chunked) DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<false, true>, mp));
+  else DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<false, false>, mp));
   DAAM_CUDA_TRY(cudaGetLastError());
   count_launch();
   return DAAM_OK;
