@@ -70,25 +70,30 @@ def emit(line: dict):
 # workload description
 # --------------------------------------------------------------------------------------------------------------------
 def traced_layers(workload: str):
-    """(hw, heads) of every traced layer in the reference's layer_idx order, head_dim 64."""
+    """(hw, heads, head_dim) of every traced layer in the reference's layer_idx order."""
     if workload == 'sd21':
-        return [(256, 20)] * 3 + [(1024, 10)] * 3 + [(4096, 5)] * 3 + [(4096, 5)] * 2 + [(1024, 10)] * 2 + [(256, 20)] * 2
+        shapes = [(256, 20)] * 3 + [(1024, 10)] * 3 + [(4096, 5)] * 3 + [(4096, 5)] * 2 + [(1024, 10)] * 2 + [(256, 20)] * 2
+        return [(hw, h, 64) for hw, h in shapes]
     if workload == 'sdxl':   # 60 layers (default trace, no mid block): up 3x10 @32^2, 3x2 @64^2; down 2x2 @64^2, 2x10 @32^2
-        return [(1024, 20)] * 30 + [(4096, 10)] * 6 + [(4096, 10)] * 4 + [(1024, 20)] * 20
+        shapes = [(1024, 20)] * 30 + [(4096, 10)] * 6 + [(4096, 10)] * 4 + [(1024, 20)] * 20
+        return [(hw, h, 64) for hw, h in shapes]
+    if workload == 'sd15':   # SD-1.x: 8 heads everywhere, head dims 160 / 80 / 40
+        shapes = [(256, 160)] * 3 + [(1024, 80)] * 3 + [(4096, 40)] * 3 + [(4096, 40)] * 2 + [(1024, 80)] * 2 + [(256, 160)] * 2
+        return [(hw, 8, d) for hw, d in shapes]
     raise ValueError(workload)
 
 
 def px_per_step(layers, n_prompts=1):
-    return n_prompts * sum(h * TOKENS * hw for hw, h in layers)
+    return n_prompts * sum(h * TOKENS * hw for hw, h, _ in layers)
 
 
 def literal_px_per_step(layers, n_prompts=1, x=64):
     return n_prompts * len(layers) * TOKENS * x * x      # BASELINE-literal "layers x tokens x 64^2"
 
 
-def algorithmic_bytes_per_step(layers, n_prompts=1, esize=2, d=64):
+def algorithmic_bytes_per_step(layers, n_prompts=1, esize=2):
     """Q + K in the config dtype, fp32 accumulator read + write (conditional half only)."""
-    return n_prompts * sum(h * hw * d * esize + h * TOKENS * d * esize + h * TOKENS * hw * 4 * 2 for hw, h in layers)
+    return n_prompts * sum(h * hw * d * esize + h * TOKENS * d * esize + h * TOKENS * hw * 4 * 2 for hw, h, d in layers)
 
 
 def measured_peak():
@@ -191,11 +196,11 @@ def build_sets(layers, n_prompts, dtype, n_sets, seed):
     sets = []
     for _ in range(n_sets):
         descs, keep = [], []
-        for hw, heads in layers:
-            q = torch.randn(2 * n_prompts, hw, heads * 64, generator=g, device='cuda', dtype=torch.float32).to(dtype)
-            k = torch.randn(2 * n_prompts, TOKENS, heads * 64, generator=g, device='cuda', dtype=torch.float32).to(dtype)
+        for hw, heads, d in layers:
+            q = torch.randn(2 * n_prompts, hw, heads * d, generator=g, device='cuda', dtype=torch.float32).to(dtype)
+            k = torch.randn(2 * n_prompts, TOKENS, heads * d, generator=g, device='cuda', dtype=torch.float32).to(dtype)
             acc = ops.new_accumulator(n_prompts, heads, hw, 'cuda')
-            descs.append(ops.make_layer_desc(q, k, acc, heads, 0.125))
+            descs.append(ops.make_layer_desc(q, k, acc, heads, d ** -0.5))
             keep.append((q, k, acc))
         sets.append((ops.pack(descs), keep))
     return sets
@@ -370,13 +375,13 @@ def leg_cpu_baseline(layers, budget_s=12.0):
     """Oracle port of the hot-path stages on the host cores: baddbmm+softmax (a3), unravel (a4), per-head update (a6)."""
     from oracle import daam_oracle as O
     g = torch.Generator().manual_seed(0)
-    qs = [torch.randn(2, hw, h * 64, generator=g) for hw, h in layers]
-    ks = [torch.randn(2, TOKENS, h * 64, generator=g) for hw, h in layers]
+    qs = [torch.randn(2, hw, h * d, generator=g) for hw, h, d in layers]
+    ks = [torch.randn(2, TOKENS, h * d, generator=g) for hw, h, d in layers]
     store = O.OracleHeatMaps()
 
     def one_step():
-        for i, ((hw, h), q, k) in enumerate(zip(layers, qs, ks)):
-            maps = O.port_layer_step(q, k, h, 0.125)
+        for i, ((hw, h, d), q, k) in enumerate(zip(layers, qs, ks)):
+            maps = O.port_layer_step(q, k, h, d ** -0.5)
             for head, m in enumerate(maps):
                 store.update(1, i, head, m)
 
@@ -402,9 +407,9 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from daam_b200.synthetic import SD21_SPEC, SDXL_SPEC, make_pipeline
+    from daam_b200.synthetic import SD15_SPEC, SD21_SPEC, SDXL_SPEC, make_pipeline
     from oracle import daam_oracle as O
-    spec = SD21_SPEC if args.workload == 'sd21' else SDXL_SPEC
+    spec = {'sd21': SD21_SPEC, 'sdxl': SDXL_SPEC, 'sd15': SD15_SPEC}[args.workload]
     layers = traced_layers(args.workload)
     pipe = make_pipeline(spec, body='skeleton', dtype=torch.float32, device='cpu', seed=0)
     prompt = 'a photo of a dog chasing a red ball on the beach at sunset'
@@ -443,7 +448,9 @@ def run_reference(args):
 
 
 def workload_name(args):
-    base = {'sd21': 'random-init SD-2.1-base UNet shapes, 64x64 latent, 77 tokens, 15 traced cross-attn layers/step',
+    base = {'sd15': 'random-init SD-1.5 UNet shapes (8 heads, head dims 40/80/160), 64x64 latent, 77 tokens, 15 traced '
+                    'cross-attn layers/step',
+            'sd21': 'random-init SD-2.1-base UNet shapes, 64x64 latent, 77 tokens, 15 traced cross-attn layers/step',
             'sdxl': 'random-init SDXL UNet shapes, 128x128 latent, 77 tokens, 60 traced cross-attn layers/step'}
     return f'{base[args.workload]}, {args.prompts} prompt(s)/GPU, {args.dtype}'
 
@@ -455,7 +462,7 @@ def main():
     ap.add_argument('--steps', type=int, default=50)       # BASELINE configs[1]: 50 denoising steps
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='daam_b200', choices=['daam_b200', 'reference'])
-    ap.add_argument('--workload', default='sd21', choices=['sd21', 'sdxl'])
+    ap.add_argument('--workload', default='sd21', choices=['sd21', 'sdxl', 'sd15'])
     ap.add_argument('--prompts', type=int, default=1, help='prompts per GPU traced together (batch_prompts mode)')
     ap.add_argument('--dtype', default=None, choices=['bf16', 'fp16', 'fp32'])
     ap.add_argument('--skip-overhead', action='store_true')
@@ -463,7 +470,7 @@ def main():
     ap.add_argument('--skip-eager', action='store_true', help='skip the eager (no CUDA graph) e2e leg')
     args = ap.parse_args()
     if args.dtype is None:
-        args.dtype = 'bf16' if args.workload == 'sd21' else 'fp16'
+        args.dtype = {'sd21': 'bf16', 'sdxl': 'fp16', 'sd15': 'fp32'}[args.workload]   # sd15: the reference's default load
     args.warmup = max(3, args.warmup)
     capture_stdout()
 
@@ -472,9 +479,9 @@ def main():
         return
 
     from daam_b200 import _native
-    from daam_b200.synthetic import SD21_SPEC, SDXL_SPEC
+    from daam_b200.synthetic import SD15_SPEC, SD21_SPEC, SDXL_SPEC
     dtype = {'bf16': torch.bfloat16, 'fp16': torch.float16, 'fp32': torch.float32}[args.dtype]
-    spec = SD21_SPEC if args.workload == 'sd21' else SDXL_SPEC
+    spec = {'sd21': SD21_SPEC, 'sdxl': SDXL_SPEC, 'sd15': SD15_SPEC}[args.workload]
     layers = traced_layers(args.workload)
     D = Dist(args.gpus)
     _native.load()

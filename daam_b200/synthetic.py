@@ -31,7 +31,7 @@ import torch.nn.functional as F
 
 __all__ = [
     'SyntheticAttention', 'SDPAProcessor', 'SyntheticUNet', 'SyntheticPipeline', 'WhitespaceTokenizer',
-    'UNetSpec', 'SD21_SPEC', 'SDXL_SPEC', 'TINY_SPEC', 'make_pipeline',
+    'UNetSpec', 'SD21_SPEC', 'SDXL_SPEC', 'SD15_SPEC', 'TINY_SPEC', 'TINY15_SPEC', 'make_pipeline',
 ]
 
 
@@ -296,7 +296,7 @@ class UNetSpec:
     heads: Sequence[int]
     depth: Sequence[int]
     cross_attention_dim: int
-    dim_head: int = 64
+    dim_head: Optional[int] = 64              # None: SD-1.x style, head_dim = channels // heads
     layers_per_block: int = 2
     mid_depth: Optional[int] = None          # transformer depth of the mid block (None: same as last block, min 1)
     in_channels: int = 4
@@ -307,8 +307,12 @@ class UNetSpec:
 # public unet/config.json values of stabilityai/stable-diffusion-2-1-base and stabilityai/stable-diffusion-xl-base-1.0
 SD21_SPEC = UNetSpec('sd21-base', 64, (320, 640, 1280, 1280), (5, 10, 20, 20), (1, 1, 1, 0), 1024)
 SDXL_SPEC = UNetSpec('sdxl-base', 128, (320, 640, 1280), (5, 10, 20), (0, 2, 10), 2048, mid_depth=10)
+# runwayml/stable-diffusion-v1-5: 8 heads at every level, head dims 40 / 80 / 160
+SD15_SPEC = UNetSpec('sd15', 64, (320, 640, 1280, 1280), (8, 8, 8, 8), (1, 1, 1, 0), 768, dim_head=None)
 # a small tree with the SD-2.1 topology (15 located layers, factors 1/2/4, mid layer at factor 8) for CPU tests
 TINY_SPEC = UNetSpec('tiny', 64, (64, 128, 128, 128), (1, 2, 2, 2), (1, 1, 1, 0), 96)
+# the same topology with SD-1.x style head dims (40 / 80 / 80)
+TINY15_SPEC = UNetSpec('tiny15', 64, (80, 160, 160, 160), (2, 2, 2, 2), (1, 1, 1, 0), 96, dim_head=None)
 
 
 class SyntheticUNet(nn.Module):
@@ -330,8 +334,8 @@ class SyntheticUNet(nn.Module):
         def attn_cfg(i):
             if spec.depth[i] == 0:
                 return None
-            return dict(heads=spec.heads[i], dim_head=spec.dim_head, ctx_dim=spec.cross_attention_dim,
-                        depth=spec.depth[i], upcast_attention=spec.upcast_attention)
+            return dict(heads=spec.heads[i], dim_head=spec.dim_head or ch[i] // spec.heads[i],
+                        ctx_dim=spec.cross_attention_dim, depth=spec.depth[i], upcast_attention=spec.upcast_attention)
 
         downs, skip_ch = [], [ch[0]]
         cin = ch[0]
@@ -345,7 +349,8 @@ class SyntheticUNet(nn.Module):
 
         mid_depth = spec.mid_depth if spec.mid_depth is not None else max(1, spec.depth[-1])
         self.mid_block = UNetMidBlock2DCrossAttn(ch[-1], temb_dim, full, dict(
-            heads=spec.heads[-1], dim_head=spec.dim_head, ctx_dim=spec.cross_attention_dim, depth=mid_depth,
+            heads=spec.heads[-1], dim_head=spec.dim_head or ch[-1] // spec.heads[-1],
+            ctx_dim=spec.cross_attention_dim, depth=mid_depth,
             upcast_attention=spec.upcast_attention))
 
         ups = []

@@ -200,4 +200,6 @@ def test_bench_workload_definitions_match_the_survey():
     assert abs(bench.algorithmic_bytes_per_step(sd21, esize=4) / 1e6 - 159.71) < 0.01
     # SDXL default trace: 10 layers at 64^2 with 10 heads (30.57 MB each), 50 at 32^2 with 20 heads (15.43 MB each)
     assert abs(bench.algorithmic_bytes_per_step(sdxl, esize=2) / 1e6 - (10 * 30.57 + 50 * 15.43)) < 0.5
+    sd15 = bench.traced_layers('sd15')
+    assert len(sd15) == 15 and {h for _, h, _ in sd15} == {8} and {d for _, _, d in sd15} == {40, 80, 160}
     assert bench.px_per_step(sd21, n_prompts=8) == 8 * 13_798_400

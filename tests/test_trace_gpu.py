@@ -269,3 +269,23 @@ def test_collection_interface_update_and_to_experiment(tmp_path):
     exp.save()
     back = GenerationExperiment.load(tmp_path / 'gen0', map_location='cpu')
     assert torch.equal(back.global_heat_map, ref.cpu()) and back.seed == 1
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.float16, 4e-4)])
+def test_sd1x_style_pipeline(dtype, tol):
+    """SD-1.x style UNet (head_dim = channels // heads: 40 / 80 / 80): the tracer picks the K-chunked tcgen05 path; parity
+    with the oracle on the identical Q/K the hooks saw."""
+    from daam_b200.synthetic import TINY15_SPEC
+    pipe = make_pipeline(TINY15_SPEC, dtype=dtype, device=DEV, seed=3)
+    with trace(pipe) as tc:
+        rec = Recorder(tc)
+        pipe(PROMPT, num_inference_steps=2, generator=torch.Generator().manual_seed(11))
+        store = rec.oracle_store()
+        got = dict(tc.all_heat_maps)
+        assert len(got) == 30                     # 15 layers x 2 heads
+        for key, ref in store:
+            assert rel_err(got[key], ref) < tol, key
+        n_tok = len(pipe.tokenizer.tokenize(PROMPT))
+        ref = O.port_global_heat_map(store, 4096, n_tok)
+        assert rel_err(tc.compute_global_heat_map().heat_maps, ref) < tol
+    assert {c[1].shape[-1] // c[4] for c in rec.calls} == {40, 80}
