@@ -288,4 +288,4 @@ def test_sd1x_style_pipeline(dtype, tol):
         n_tok = len(pipe.tokenizer.tokenize(PROMPT))
         ref = O.port_global_heat_map(store, 4096, n_tok)
         assert rel_err(tc.compute_global_heat_map().heat_maps, ref) < tol
-    assert {c[1].shape[-1] // c[4] for c in rec.calls} == {40, 80}
+    assert {c[2].shape[-1] // c[4] for c in rec.calls} == {40, 80}
