@@ -1,16 +1,18 @@
-"""Hook plumbing: context-managed monkey patching and the walker that finds a UNet's cross-attention layers.
+"""Context-managed monkey patching (the reference's L0, ``/root/reference/daam/hook.py:22-86``).
 
-Behavioural mirror of the reference's L0 (``/root/reference/daam/hook.py``): same class and method names, same
-exceptions (``RuntimeError('Already hooked module')`` / ``('Module is not hooked')``, hook.py:36-37, 46-47), and --
-what the hot path depends on -- the same layer enumeration order, which defines ``layer_idx`` (hook.py:95-127):
-``up_blocks`` first, then ``down_blocks``, then optionally ``mid_block``.
+``ObjectHooker`` wraps one object: ``hook()`` runs the subclass' ``_hook_impl`` (which typically calls
+``monkey_patch``), ``unhook()`` puts every replaced attribute back and runs ``_unhook_impl``; both are also reachable
+as a ``with`` block. ``AggregateHooker`` does the same for a list of hookers. Public names, call signatures and the
+two error messages (``'Already hooked module'``, ``'Module is not hooked'``, hook.py:36-37, 46-47) are the
+reference's, because user code and the tracer rely on them; the layer walker lives in ``locate.py`` and is re-exported
+here under its reference name.
 """
 from __future__ import annotations
 
 import functools
-from typing import Generic, List, Optional, Set, TypeVar
+from typing import Any, Callable, Dict, Generic, List, TypeVar
 
-import torch.nn as nn
+from .locate import ModuleLocator, UNetCrossAttentionLocator
 
 __all__ = ['ObjectHooker', 'ModuleLocator', 'AggregateHooker', 'UNetCrossAttentionLocator']
 
@@ -18,56 +20,53 @@ ModuleType = TypeVar('ModuleType')
 ModuleListType = TypeVar('ModuleListType', bound=List)
 
 
-class ModuleLocator(Generic[ModuleType]):
-    def locate(self, model: nn.Module) -> List[ModuleType]:
-        raise NotImplementedError
-
-
 class ObjectHooker(Generic[ModuleType]):
-    """Owns one object; ``hook()`` applies patches, ``unhook()`` restores every attribute ``monkey_patch`` replaced."""
-
     def __init__(self, module: ModuleType):
         self.module: ModuleType = module
-        self.hooked = False
-        self._originals = {}
+        self.hooked: bool = False
+        self._replaced: Dict[str, Any] = {}     # attribute name -> what it was before monkey_patch
 
-    def __enter__(self):
-        self.hook()
-        return self
-
-    def __exit__(self, exc_type, exc_val, exc_tb):
-        self.unhook()
-
+    # -- lifecycle ----------------------------------------------------------------------------------------------------
     def hook(self):
         if self.hooked:
             raise RuntimeError('Already hooked module')
-        self._originals = {}
         self.hooked = True
+        self._replaced = {}
         self._hook_impl()
         return self
 
     def unhook(self):
         if not self.hooked:
             raise RuntimeError('Module is not hooked')
-        for name, fn in self._originals.items():
-            setattr(self.module, name, fn)
+        while self._replaced:
+            name, original = self._replaced.popitem()
+            setattr(self.module, name, original)
         self.hooked = False
         self._unhook_impl()
         return self
 
-    def monkey_patch(self, fn_name: str, fn, strict: bool = True):
-        """Replace ``module.fn_name`` by ``fn(module, ...)``; a missing attribute is ignored unless ``strict``."""
-        try:
-            self._originals[fn_name] = getattr(self.module, fn_name)
-        except AttributeError:
+    def __enter__(self):
+        return self.hook()
+
+    def __exit__(self, exc_type, exc_val, exc_tb):
+        self.unhook()
+
+    # -- patching helpers for subclasses -------------------------------------------------------------------------------
+    def monkey_patch(self, fn_name: str, fn: Callable, strict: bool = True):
+        """``module.fn_name`` becomes ``fn(module, *args, **kwargs)``. With ``strict=False`` an attribute the object
+        does not have is skipped silently (SDXL pipelines have no safety checker)."""
+        if not hasattr(self.module, fn_name):
             if strict:
-                raise
+                raise AttributeError(f'{type(self.module).__name__!r} object has no attribute {fn_name!r}')
             return
+        self._replaced.setdefault(fn_name, getattr(self.module, fn_name))
         setattr(self.module, fn_name, functools.partial(fn, self.module))
 
     def monkey_super(self, fn_name: str, *args, **kwargs):
-        return self._originals[fn_name](*args, **kwargs)
+        """Call what ``fn_name`` was before it got patched."""
+        return self._replaced[fn_name](*args, **kwargs)
 
+    # -- to be provided by subclasses -------------------------------------------------------------------------------------
     def _hook_impl(self):
         raise NotImplementedError
 
@@ -76,40 +75,15 @@ class ObjectHooker(Generic[ModuleType]):
 
 
 class AggregateHooker(ObjectHooker[ModuleListType]):
-    """A hooker over a list of hookers."""
-
-    def _hook_impl(self):
-        for child in self.module:
-            child.hook()
-
-    def _unhook_impl(self):
-        for child in self.module:
-            child.unhook()
+    """Hooks / unhooks every hooker of ``self.module`` (a list), in order."""
 
     def register_hook(self, hook: ObjectHooker):
         self.module.append(hook)
 
+    def _hook_impl(self):
+        for member in self.module:
+            member.hook()
 
-class UNetCrossAttentionLocator(ModuleLocator):
-    """Enumerates ``attn2`` modules in the reference's order; the position in the returned list is ``layer_idx``."""
-
-    def __init__(self, restrict: Optional[Set[int]] = None, locate_middle_block: bool = False):
-        self.restrict = restrict
-        self.layer_names: List[str] = []
-        self.locate_middle_block = locate_middle_block
-
-    def locate(self, model) -> list:
-        self.layer_names.clear()
-        located = []
-        tagged = [(blk, 'up') for blk in model.up_blocks] + [(blk, 'down') for blk in model.down_blocks]
-        if self.locate_middle_block:
-            tagged.append((model.mid_block, 'mid'))
-        for block, tag in tagged:
-            if 'CrossAttn' not in type(block).__name__:
-                continue
-            layers = [tb.attn2 for transformer in block.attentions for tb in transformer.transformer_blocks]
-            for i, layer in enumerate(layers):      # the index restarts in every block: names are not unique
-                if self.restrict is None or i in self.restrict:
-                    located.append(layer)
-                    self.layer_names.append(f'{tag}-attn-{i}')
-        return located
+    def _unhook_impl(self):
+        for member in self.module:
+            member.unhook()
