@@ -332,3 +332,32 @@ def test_sd1x_head_dims_on_tensor_cores(hw, heads, d, dtype):
     ref = oracle_layer_maps(q, k, heads, d ** -0.5).unsqueeze(0)
     assert_close(mma, ref, TOL[dtype], f'mma d{d}')
     assert_close(simt, ref, TOL[dtype], f'simt d{d}')
+
+
+def test_full_size_sdxl_and_batched_step_properties():
+    """BASELINE configs 3-5 sizes: the 60 traced SDXL layers (fp16) with 2 prompts in one call, and SD-2.1 with 8 prompts
+    (bf16) -- checked through per-head sums (= steps * hw), non-negativity, and batched == per-prompt launches."""
+    import bench
+    for workload, dtype, prompts in [('sdxl', torch.float16, 2), ('sd21', torch.bfloat16, 8)]:
+        layers = bench.traced_layers(workload)
+        g = torch.Generator(device=DEV).manual_seed(5)
+        qs = [torch.randn(2 * prompts, hw, h * d, generator=g, device=DEV).to(dtype) for hw, h, d in layers]
+        ks = [torch.randn(2 * prompts, 77, h * d, generator=g, device=DEV).to(dtype) for hw, h, d in layers]
+        accs = [ops.new_accumulator(prompts, h, hw, DEV) for hw, h, d in layers]
+        descs = [ops.make_layer_desc(q, k, a, h, d ** -0.5) for q, k, a, (hw, h, d) in zip(qs, ks, accs, layers)]
+        before = _native.launch_count()
+        for _ in range(2):
+            ops.accumulate(descs, DEV)
+        torch.cuda.synchronize()
+        assert _native.launch_count() - before == 2 * -(-len(layers) // 32)      # 32 layer descriptors per launch
+        for a, (hw, h, d) in zip(accs, layers):
+            sums = a.double().sum(dim=(2, 3))
+            assert torch.allclose(sums, torch.full_like(sums, 2.0 * hw), rtol=2e-5)
+            assert (a >= 0).all()
+        for i in (0, len(layers) // 2, len(layers) - 1):       # batched launch == independent single-prompt launches
+            hw, h, d = layers[i]
+            for p in (0, prompts - 1):
+                pair_q, pair_k = torch.stack([qs[i][p], qs[i][prompts + p]]), torch.stack([ks[i][p], ks[i][prompts + p]])
+                single = ops.accumulate_layer(pair_q, pair_k, h)
+                torch.cuda.synchronize()
+                assert_close(accs[i][p], 2 * single[0], 1e-6, f'{workload} layer {i} prompt {p}')
