@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define DAAM_ABI_VERSION 1
+#define DAAM_ABI_VERSION 2          /* 2: + daam_attention_probs, daam_accumulate_probs, daam_finalize_per_key */
 #define DAAM_TOKENS 77          /* context length the reference traces (daam/trace.py:194, guard at :289) */
 #define DAAM_MAX_HEAD_DIM 160   /* SD-1.x deepest level: 1280 channels / 8 heads */
 
@@ -38,7 +38,8 @@ enum daam_status {
 enum daam_dtype { DAAM_F32 = 0, DAAM_F16 = 1, DAAM_BF16 = 2 };
 
 /* daam_accumulate flags */
-#define DAAM_ACC_AUTO        0u  /* tcgen05 path for 16-bit inputs with head_dim 64, SIMT fp32 path otherwise */
+#define DAAM_ACC_AUTO        0u  /* tcgen05 path whenever rows are 16-byte aligned (any dtype, head_dim % 8 == 0),
+                                    SIMT fp32 path otherwise */
 #define DAAM_ACC_FORCE_SIMT  1u  /* always the SIMT fp32 ("warp dot") kernel */
 #define DAAM_ACC_FORCE_MMA   2u  /* tcgen05 kernel or DAAM_E_UNSUPPORTED */
 #define DAAM_ACC_RMW_MASK   0x30u
