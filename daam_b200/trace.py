@@ -131,7 +131,8 @@ class DiffusionHeatMapHooker(AggregateHooker):
             self.flush()
         cached = self._desc_cache.get(layer_idx)
         if cached is not None and q.shape == cached[0] and q.dtype is cached[1] and q.is_contiguous() \
-                and k.is_contiguous() and self.all_heat_maps.slabs.get(layer_idx) is cached[3]:
+                and k.is_contiguous() and self.all_heat_maps.slabs.get(layer_idx) is cached[3] \
+                and q.device == cached[3].acc.device:
             _, _, desc, slab, q_off, k_off = cached
             desc.q = q.data_ptr() + q_off
             desc.k = k.data_ptr() + k_off

@@ -203,3 +203,33 @@ def test_bench_workload_definitions_match_the_survey():
     sd15 = bench.traced_layers('sd15')
     assert len(sd15) == 15 and {h for _, h, _ in sd15} == {8} and {d for _, _, d in sd15} == {40, 80, 160}
     assert bench.px_per_step(sd21, n_prompts=8) == 8 * 13_798_400
+
+
+def test_bench_clock_sampler_and_stdout_contract(capfd):
+    """The pieces of bench.py the driver parses: throttle reasons / median clock from nvidia-smi rows, and exactly one
+    JSON line on the real stdout even when libraries print to fd 1."""
+    import json
+    import os
+    import time
+    import bench
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+    s.proc = type('P', (), {'terminate': lambda self: None})()
+    now = time.time()
+    s.rows = [(now - 10, ['300', '1965', '80', '0', 'Not Active', 'Not Active', 'Not Active', 'Not Active']),
+              (now - 1.0, ['1965', '1965', '900', '99', 'Not Active', 'Not Active', 'Not Active', 'Active']),
+              (now - 0.9, ['1800', '1965', '950', '99', 'Not Active', 'Not Active', 'Not Active', 'Active']),
+              (now - 0.8, ['1900', '1965', '950', '99', 'Not Active', 'Not Active', 'Not Active', 'Not Active'])]
+    out = s.stop([(now - 2, now)])
+    assert out == {'sm_mhz': 1900.0, 'sm_max_mhz': 1965.0, 'reasons': ['sw_power_cap'], 'samples': 3}
+    bench._REAL_STDOUT = None
+    bench.capture_stdout()
+    try:
+        os.write(1, b'NCCL version banner\\n')          # a library writing to fd 1 lands on stderr
+        bench.emit({'metric': 'x', 'value': 1})
+    finally:
+        os.dup2(bench._REAL_STDOUT, 1)
+        os.close(bench._REAL_STDOUT)
+        bench._REAL_STDOUT = None
+    captured = capfd.readouterr()
+    assert captured.out.strip().splitlines() == [json.dumps({'metric': 'x', 'value': 1})]
+    assert 'NCCL version banner' in captured.err
