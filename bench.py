@@ -493,11 +493,18 @@ def main():
         e2e_ms, h2d, d2h = leg_e2e(args, spec, dtype, D, windows, cuda_graph=True)
         eager_ms = leg_e2e(args, spec, dtype, D, windows, cuda_graph=False)[0] if not args.skip_eager else float('nan')
         overhead = None
-        if not args.skip_overhead and D.rank == 0 and D.world == 1:
+        if not args.skip_overhead:       # every rank measures its own GPU (all ranks share the host's cores)
             try:
                 overhead = leg_hook_overhead(args, spec, dtype, windows)
             except Exception as e:   # reported, never silently dropped
                 overhead = {'error': repr(e)}
+            if D.world > 1 and 'overhead_ms_per_step' in overhead:
+                worst = torch.tensor([overhead['overhead_ms_per_step'], overhead['hooked_ms_per_step'],
+                                      overhead['unhooked_ms_per_step']], dtype=torch.float64, device='cuda')
+                D.dist.all_reduce(worst, op=D.dist.ReduceOp.MAX)
+                overhead['max_over_ranks'] = {'overhead_ms_per_step': round(float(worst[0]), 4),
+                                              'hooked_ms_per_step': round(float(worst[1]), 4),
+                                              'unhooked_ms_per_step': round(float(worst[2]), 4), 'ranks': D.world}
     D.barrier()
     if D.rank != 0:
         D.close()
