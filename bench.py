@@ -311,6 +311,10 @@ def leg_hook_overhead(args, spec, dtype, windows):
                 res[mode] = run(n)
                 tc.synchronize()
         base2 = run(n)
+        with trace(pipe, launch='step') as tc:       # second hooked sample after the second un-hooked one: both
+            run(5)                                    # sides get the best of two interleaved medians (host jitter)
+            res['step'] = min(res['step'], run(n))
+            tc.synchronize()
         # the same comparison with the forward replayed from a CUDA graph (no host launch cost on either side)
         def graphed():
             g = torch.cuda.CUDAGraph()
