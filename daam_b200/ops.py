@@ -5,8 +5,7 @@ hook; the parity tests and ``bench.py`` call it directly with Q/K tensors.
 """
 from __future__ import annotations
 
-import math
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 

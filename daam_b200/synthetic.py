@@ -21,7 +21,7 @@ These are fixtures: they contain no DAAM logic. The weights are random (default 
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from types import SimpleNamespace
 from typing import List, Optional, Sequence
 

@@ -23,7 +23,6 @@ Row labels (a1..a10) are SURVEY.md section 8a; every function cites the referenc
 from __future__ import annotations
 
 import functools
-import itertools
 import math
 from collections import defaultdict
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple

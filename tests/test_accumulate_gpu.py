@@ -5,7 +5,6 @@ golden vectors the verbatim reference produced. Tolerances (stated per SURVEY.md
 * fp16/bf16 inputs: the oracle is fed the same (half-rounded) values in fp32; same bound x 20 (tensor-core
   accumulation order and ex2.approx differ from torch's fp32 softmax).
 """
-import numpy as np
 import pytest
 import torch
 

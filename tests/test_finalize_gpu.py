@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from daam_b200 import _native
-from daam_b200.heatmap import GlobalHeatMap, WordHeatMap
+from daam_b200.heatmap import GlobalHeatMap
 from daam_b200.synthetic import WhitespaceTokenizer
 from oracle import daam_oracle as O
 from tests.util import golden, rel_err

@@ -151,7 +151,6 @@ def test_bad_options_are_rejected():
 
 def test_generation_experiment_roundtrip_and_reference_dump(tmp_path):
     """Same folder layout as the reference (experiment.py:140-175); dumps pickled under the reference's class path load."""
-    import pickle
     import sys
     import types
     from daam_b200 import GenerationExperiment

@@ -1,13 +1,12 @@
 """End-to-end parity through the public API: `with trace(pipe) as tc: pipe(...); tc.compute_global_heat_map()` on the
 GPU vs the oracle fed the identical Q/K the hooks saw, and (loosely) vs the reference's own run of the same pipeline."""
-import numpy as np
 import pytest
 import torch
 
-from daam_b200 import _native, ops, trace
+from daam_b200 import trace
 from daam_b200.synthetic import TINY_SPEC, make_pipeline
 from oracle import daam_oracle as O
-from tests.util import golden, oracle_layer_maps, rel_err
+from tests.util import golden, rel_err
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
