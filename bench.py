@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the cross-attention heat-map hot path (BASELINE.json metric: heat-map px/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload sd21|sdxl] [--prompts P]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload sd21|sdxl|sdxl70|sd15] [--prompts P]
 
 Workload (BASELINE.json configs[1]): random-init SD-2.1-base UNet shapes, 64x64 latent, 77 tokens, bf16, the 15 traced
 cross-attention layers of one denoising step. A bench "step" is one pass of the hot path over one step's Q/K:
@@ -77,6 +77,10 @@ def traced_layers(workload: str):
     if workload == 'sdxl':   # 60 layers (default trace, no mid block): up 3x10 @32^2, 3x2 @64^2; down 2x2 @64^2, 2x10 @32^2
         shapes = [(1024, 20)] * 30 + [(4096, 10)] * 6 + [(4096, 10)] * 4 + [(1024, 20)] * 20
         return [(hw, h, 64) for hw, h in shapes]
+    if workload == 'sdxl70':   # BASELINE configs[4]: "all 70 cross-attn layers traced" = the 60 above + the mid block's 10
+        # (located only with the tracer's locate_middle_block switch; reference: daam/trace.py:34-35, daam/hook.py:110-114,
+        # where the mid block comes last in layer order)
+        return traced_layers('sdxl') + [(1024, 20, 64)] * 10
     if workload == 'sd15':   # SD-1.x: 8 heads everywhere, head dims 160 / 80 / 40
         shapes = [(256, 160)] * 3 + [(1024, 80)] * 3 + [(4096, 40)] * 3 + [(4096, 40)] * 2 + [(1024, 80)] * 2 + [(256, 160)] * 2
         return [(hw, 8, d) for hw, d in shapes]
@@ -207,35 +211,65 @@ def build_sets(layers, n_prompts, dtype, n_sets, seed):
 
 
 def leg_value(args, layers, dtype, D: Dist, windows):
+    """K steps (one persistent launch per traced-layer pack each) between CUDA events, repeated over R blocks.
+
+    Every block is what the contract describes -- barrier + synchronize, K timed steps, synchronize + barrier -- and the
+    reported time is the median block (max over ranks per block). The launches of a block are queued behind a short
+    spin kernel so that the device executes them back to back: the figure is device throughput, not host launch pacing
+    (8 Python processes share one host at N=8)."""
     from daam_b200 import _native, ops
-    set_bytes = algorithmic_bytes_per_step(layers, args.prompts) - px_per_step(layers, args.prompts) * 4  # acc counted once
-    n_sets = max(2, -(-int(320e6) // max(1, set_bytes)))      # working set >= 320 MB > 126 MB L2
+    n_sets, _ = value_sets(layers, args.prompts)               # working set >= 320 MB > 126 MB L2
     sets = build_sets(layers, args.prompts, dtype, n_sets, 1234 + D.rank)
     stream = torch.cuda.current_stream()
+    flags = _native.ACC_AUTO | _native.ACC_EARLY_LOADS       # Q/K are resident inputs: complete long before any launch
     for i in range(args.warmup):
-        ops.accumulate(sets[i % n_sets][0], 'cuda', stream)
+        ops.accumulate(sets[i % n_sets][0], 'cuda', stream, flags)
     torch.cuda.synchronize()
-    D.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    blocks = max(10, -(-200 // args.steps))
+    gate_cycles = int(max(2.0, args.steps * 0.04) * 1.9e6)     # ~max(2 ms, 40 us per launch) at 1.9 GHz
     launches0 = _native.launch_count()
-    t0 = time.time()
-    e0.record(stream)
-    for i in range(args.steps):
-        ops.accumulate(sets[i % n_sets][0], 'cuda', stream)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    D.barrier()
-    torch.cuda.synchronize()
-    windows.append((t0, time.time()))
-    ms = D.max_ms(e0.elapsed_time(e1))
-    launches = _native.launch_count() - launches0
+    block_ms, step = [], args.warmup
+    for _ in range(blocks):
+        D.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        torch.cuda._sleep(gate_cycles)
+        e0.record(stream)
+        for _k in range(args.steps):
+            ops.accumulate(sets[step % n_sets][0], 'cuda', stream, flags)
+            step += 1
+        e1.record(stream)
+        torch.cuda.synchronize()
+        D.barrier()
+        torch.cuda.synchronize()
+        block_ms.append(e0.elapsed_time(e1))
+        if len(block_ms) == 1:
+            t_first = t0
+    windows.append((t_first, time.time()))
+    launches = (_native.launch_count() - launches0) // blocks          # per K-step block
+    mine = torch.tensor(block_ms, dtype=torch.float64, device='cuda')
+    if D.world > 1:
+        allr = torch.empty(D.world, blocks, dtype=torch.float64, device='cuda')
+        D.dist.all_gather_into_tensor(allr, mine.unsqueeze(0))
+    else:
+        allr = mine.unsqueeze(0)
+    per_block_max = allr.max(dim=0).values                              # max over ranks, block by block
+    ms = float(per_block_max.median())
+    us = allr / args.steps * 1e3                                        # per-launch-step, per rank and block
+    stats = {'blocks': blocks, 'steps_per_block': args.steps,
+             'us_per_step_median_block_max_over_ranks': round(ms / args.steps * 1e3, 3),
+             'us_per_step_best_block_max_over_ranks': round(float(per_block_max.min()) / args.steps * 1e3, 3),
+             'us_per_step_worst_block_max_over_ranks': round(float(per_block_max.max()) / args.steps * 1e3, 3),
+             'per_rank_us_per_step': [{'rank': r, 'min': round(float(us[r].min()), 3),
+                                       'median': round(float(us[r].median()), 3), 'max': round(float(us[r].max()), 3)}
+                                      for r in range(D.world)]}
     # sanity: the timed work really accumulated (softmax rows sum to 1 -> each head gained hw per visit)
     q, k, acc = sets[0][1][0]
-    visits = len(range(0, args.warmup, n_sets)) + len(range(0, args.steps, n_sets))
+    visits = len(range(0, step, n_sets))
     got = float(acc[0, 0].double().sum())
     assert abs(got - visits * acc.shape[-1]) < 1e-3 * got, (got, visits)
-    return ms, launches, n_sets
+    return ms, launches, n_sets, stats
 
 
 def leg_e2e(args, spec, dtype, D: Dist, windows, cuda_graph=True):
@@ -243,44 +277,67 @@ def leg_e2e(args, spec, dtype, D: Dist, windows, cuda_graph=True):
     ``cuda_graph`` the pipeline replays the step's device work (UNet + the tracer's kernel) from a CUDA graph."""
     from daam_b200 import trace
     from daam_b200.distributed import gather_heat_maps
-    from daam_b200.synthetic import make_pipeline
-    pipe = make_pipeline(spec, body='skeleton', dtype=dtype, device='cuda', seed=D.rank, init_on_device=True,
-                         cuda_graph=cuda_graph)
+    from daam_b200.testing.synthetic import make_pipeline
+    mid = args.workload == 'sdxl70'
     prompts = ['a photo of a dog chasing a red ball on the beach at sunset'] * args.prompts
     prompt_arg = prompts[0] if args.prompts == 1 else prompts
-    out_h = None
-    with trace(pipe, batch_prompts=args.prompts > 1) as tc:
-        pipe(prompt_arg, num_inference_steps=max(3, args.warmup))     # also captures the step graph
-        tc.compute_global_heat_map()
-        torch.cuda.synchronize()
-        D.barrier()
-        torch.cuda.synchronize()
-        t0 = time.time()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        pipe(prompt_arg, num_inference_steps=args.steps)
-        maps = [tc.compute_global_heat_map(prompt_idx=i).heat_maps for i in range(args.prompts)]
-        if D.world > 1:   # the one optional collective: finished maps to every rank (1.26 MB per prompt)
-            allmaps = gather_heat_maps(maps, args.prompts * D.world, maps[0].shape[-1])
-        else:
-            allmaps = torch.stack([m for m in maps])
-        out_h = allmaps.to('cpu', non_blocking=False)          # D2H of the result
-        e1.record()
-        torch.cuda.synchronize()
-        D.barrier()
-        torch.cuda.synchronize()
-        windows.append((t0, time.time()))
-    ms = D.max_ms(e0.elapsed_time(e1))
-    h2d = pipe.h2d_bytes_per_step
-    d2h = pipe.d2h_bytes_per_step + out_h.numel() * 4 / max(1, args.steps) / max(1, D.world)
+
+    def generate(seed, steps, timed):
+        pipe = make_pipeline(spec, body='skeleton', dtype=dtype, device='cuda', seed=seed, init_on_device=True,
+                             cuda_graph=cuda_graph)
+        with trace(pipe, batch_prompts=args.prompts > 1, locate_middle_block=mid) as tc:
+            pipe(prompt_arg, num_inference_steps=max(3, args.warmup))     # also captures the step graph
+            tc.compute_global_heat_map()
+            torch.cuda.synchronize()
+            if not timed:
+                pipe(prompt_arg, num_inference_steps=steps)
+                return [tc.compute_global_heat_map(prompt_idx=i).heat_maps for i in range(args.prompts)], None
+            D.barrier()
+            torch.cuda.synchronize()
+            t0 = time.time()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pipe(prompt_arg, num_inference_steps=steps)
+            maps = [tc.compute_global_heat_map(prompt_idx=i).heat_maps for i in range(args.prompts)]
+            if D.world > 1:   # the one optional collective: finished maps to every rank (1.26 MB per prompt)
+                allmaps = gather_heat_maps(maps, args.prompts * D.world, maps[0].shape[-1])
+            else:
+                allmaps = torch.stack([m for m in maps])
+            out_h = allmaps.to('cpu', non_blocking=False)          # D2H of the result
+            e1.record()
+            torch.cuda.synchronize()
+            D.barrier()
+            torch.cuda.synchronize()
+            windows.append((t0, time.time()))
+            return maps, (e0.elapsed_time(e1), pipe.h2d_bytes_per_step, pipe.d2h_bytes_per_step, out_h)
+
+    maps, (ms_local, h2d, d2h_step, out_h) = generate(D.rank, args.steps, True)
+    ms = D.max_ms(ms_local)
+    d2h = d2h_step + out_h.numel() * 4 / max(1, args.steps) / max(1, D.world)
     assert torch.isfinite(out_h).all() and float(out_h.sum()) > 0
-    return ms, h2d, d2h
+    # gather ORDER check (untimed): prompt j of rank r must sit at row r + j * world. Rank 0 re-generates rank 1's first
+    # prompt itself (same seed -> same weights and inputs; every kernel on the path is deterministic) and compares.
+    order = None
+    if D.world > 1 and D.rank == 0 and cuda_graph:
+        own = torch.stack([m.cpu() for m in maps])
+        rows = out_h.shape[1]
+        same_own = all(torch.equal(out_h[j * D.world][:m.shape[0]], m.cpu()) for j, m in enumerate(maps))
+        foreign, _ = generate(1, args.steps, False)
+        f = foreign[0].cpu()
+        got = out_h[1][:f.shape[0]]
+        err = float((got - f).abs().max() / f.abs().max())
+        differs = float((out_h[0][:f.shape[0]] - f).abs().max() / f.abs().max())
+        order = {'own_rows_bit_equal': bool(same_own), 'rank1_prompt0_rel_err_vs_recomputation_on_rank0': err,
+                 'rank0_vs_rank1_maps_rel_diff': differs}
+        assert same_own and err < 1e-4 and differs > 1e-3, f'gathered maps are out of order: {order}'
+        del own, rows
+    return ms, h2d, d2h, order
 
 
 def leg_hook_overhead(args, spec, dtype, windows):
     """Hooked vs un-hooked forward of the full-cost synthetic UNet, CUDA-event timed, median over steps."""
     from daam_b200 import trace
-    from daam_b200.synthetic import make_pipeline
+    from daam_b200.testing.synthetic import make_pipeline
     pipe = make_pipeline(spec, body='full', dtype=dtype, device='cuda', seed=0, init_on_device=True)
     n = 20
     spec_ = pipe.unet.spec
@@ -305,13 +362,14 @@ def leg_hook_overhead(args, spec, dtype, windows):
         run(5)
         base = run(n)
         res = {}
+        mid = args.workload == 'sdxl70'
         for mode in ('step', 'layer'):
-            with trace(pipe, launch=mode) as tc:
+            with trace(pipe, launch=mode, locate_middle_block=mid) as tc:
                 run(5)
                 res[mode] = run(n)
                 tc.synchronize()
         base2 = run(n)
-        with trace(pipe, launch='step') as tc:       # second hooked sample after the second un-hooked one: both
+        with trace(pipe, launch='step', locate_middle_block=mid) as tc:       # second hooked sample after the second un-hooked one: both
             run(5)                                    # sides get the best of two interleaved medians (host jitter)
             res['step'] = min(res['step'], run(n))
             tc.synchronize()
@@ -336,7 +394,7 @@ def leg_hook_overhead(args, spec, dtype, windows):
         gres = {}
         try:
             gres['unhooked'] = graphed()
-            with trace(pipe) as tc:
+            with trace(pipe, locate_middle_block=mid) as tc:
                 run(2)                       # eager steps allocate the slabs before capture
                 gres['hooked'] = graphed()
                 tc.synchronize()
@@ -357,20 +415,24 @@ def leg_hook_overhead(args, spec, dtype, windows):
             'model': f'{spec.name} full-body synthetic UNet, CFG batch 2, {str(dtype).split(".")[-1]}, median of {n} forwards'}
 
 
-def pick_cpu_threads(step_fn):
-    """Give the CPU arm its best shot: torch's intra-op pool at the thread count (<= all cores) that runs one step of
-    the path fastest on this box (many-core hosts lose time to oversubscription on the path's small ops)."""
+def pick_cpu_threads(step_fn, budget_s=20.0):
+    """Give the CPU arm its best shot: torch's intra-op pool at the thread count that runs one step of the path fastest
+    on this box. Candidates stop at 32 threads (the path's ops are small: on the many-core GPU hosts 64+ threads only
+    lose time to oversubscription -- 16 of 128 won in round 1) and the probe stops at `budget_s` of wall clock."""
     cores = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
-    best, best_t = cores, float('inf')
+    cands = sorted({min(c, cores) for c in (8, 16, 32)})
+    best, best_t, t_start = cands[0], float('inf'), time.time()
     for c in cands:
         torch.set_num_threads(c)
-        step_fn()                      # warm the pool
+        if c == cands[0]:
+            step_fn()                  # first touch: page in weights, start the pool
         t = time.time()
         step_fn()
         dt = time.time() - t
         if dt < best_t:
             best, best_t = c, dt
+        if time.time() - t_start > budget_s:
+            break
     torch.set_num_threads(best)
     return best
 
@@ -407,56 +469,102 @@ def leg_cpu_baseline(layers, budget_s=12.0):
 # reference arm
 # --------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
-    """The reference's own CPU hook path (op-for-op port; `oracle/` is the only thing executed) through the pipeline API."""
+    """The reference's own hook path through the pipeline API (`oracle/` is the only thing executed: OracleTrace, the
+    op-for-op port of daam/trace.py's hooks that tests/test_oracle_vs_reference.py pins bit-equal to the verbatim
+    reference). Default: on this box's host cores in fp32 -- the contract's reference arm. ``--ref-device cuda`` runs
+    the same torch-eager reference hooks on the GPU in the pipeline dtype instead (what a user of the reference gets on
+    this box; a secondary figure recorded under profiles/, never what the driver's ratio is built on)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from daam_b200.synthetic import SD15_SPEC, SD21_SPEC, SDXL_SPEC, make_pipeline
+    from daam_b200.testing.synthetic import make_pipeline
     from oracle import daam_oracle as O
-    spec = {'sd21': SD21_SPEC, 'sdxl': SDXL_SPEC, 'sd15': SD15_SPEC}[args.workload]
-    layers = traced_layers(args.workload)
-    pipe = make_pipeline(spec, body='skeleton', dtype=torch.float32, device='cpu', seed=0)
-    prompt = 'a photo of a dog chasing a red ball on the beach at sunset'
+    spec, layers = workload_spec(args.workload), traced_layers(args.workload)
+    on_gpu = args.ref_device == 'cuda'
+    dtype = {'bf16': torch.bfloat16, 'fp16': torch.float16, 'fp32': torch.float32}[args.dtype] if on_gpu else torch.float32
+    pipe = make_pipeline(spec, body='skeleton', dtype=dtype, device=args.ref_device, seed=0, init_on_device=on_gpu)
+    prompts = ['a photo of a dog chasing a red ball on the beach at sunset'] * args.prompts
+    if args.prompts != 1:
+        raise SystemExit('the reference traces one prompt per generation (daam/trace.py:172-173): use --prompts 1')
+    prompt = prompts[0]
     budget = 150.0
-    with torch.no_grad(), O.OracleTrace(pipe) as ot:
-        pick_cpu_threads(lambda: pipe(prompt, num_inference_steps=1))
+    sync = torch.cuda.synchronize if on_gpu else (lambda: None)
+    kwargs = {'locate_middle_block': True} if args.workload == 'sdxl70' else {}
+    with torch.no_grad(), O.OracleTrace(pipe, **kwargs) as ot:
+        if not on_gpu:
+            pick_cpu_threads(lambda: pipe(prompt, num_inference_steps=1))
         t = time.time()
         pipe(prompt, num_inference_steps=1)
         ot.compute_global_heat_map()
+        sync()
         step_cost = time.time() - t
         warm = min(args.warmup, max(0, int(20.0 / step_cost) - 1))
         if warm:
             pipe(prompt, num_inference_steps=warm)
         steps = max(1, min(args.steps, int(budget / step_cost)))
+        sync()
         t0 = time.time()
         pipe(prompt, num_inference_steps=steps)
+        sync()
         t_steps = time.time() - t0
-        ot.compute_global_heat_map()
+        maps = ot.compute_global_heat_map().heat_maps.cpu()
         dt = time.time() - t0
+    assert torch.isfinite(maps.float()).all()
     ms = dt / steps * 1e3
     value = px_per_step(layers) * steps / dt
+    where = (f'on the GPU ({torch.cuda.get_device_name(0)}, torch eager, {args.dtype})' if on_gpu
+             else f'on {torch.get_num_threads()} host threads, fp32')
     sample = (f'{steps} of the requested {args.steps} steps (bounded to ~{budget:.0f} s; the path has no step-dependent '
-              f'cost) of the {spec.name} cross-attention skeleton on CPU fp32 through OracleTrace (port of '
-              f'daam/trace.py hooks), + one compute_global_heat_map; hooked forward {t_steps / steps * 1e3:.0f} ms/step')
+              f'cost) of the {spec.name} cross-attention skeleton {where} through OracleTrace (port of '
+              f'daam/trace.py hooks), + one compute_global_heat_map; hooked forward {t_steps / steps * 1e3:.1f} ms/step')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args), 'px_per_step': px_per_step(layers), 'steps_timed': steps},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                         'sample': sample},
+        'dtype': args.dtype if on_gpu else 'f32', 'data': 'synthetic',
+        'config': shared_config(args, layers, int(os.environ.get('WORLD_SIZE', '1'))),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': 0 if on_gpu else torch.get_num_threads(),
+                         'kind': 'port', 'sample': sample, 'device': args.ref_device, 'steps_timed': steps},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     emit(line)
 
 
+def workload_spec(workload):
+    from daam_b200.testing.synthetic import SD15_SPEC, SD21_SPEC, SDXL_SPEC
+    return {'sd21': SD21_SPEC, 'sdxl': SDXL_SPEC, 'sdxl70': SDXL_SPEC, 'sd15': SD15_SPEC}[workload]
+
+
 def workload_name(args):
     base = {'sd15': 'random-init SD-1.5 UNet shapes (8 heads, head dims 40/80/160), 64x64 latent, 77 tokens, 15 traced '
                     'cross-attn layers/step',
             'sd21': 'random-init SD-2.1-base UNet shapes, 64x64 latent, 77 tokens, 15 traced cross-attn layers/step',
-            'sdxl': 'random-init SDXL UNet shapes, 128x128 latent, 77 tokens, 60 traced cross-attn layers/step'}
+            'sdxl': 'random-init SDXL UNet shapes, 128x128 latent, 77 tokens, 60 traced cross-attn layers/step',
+            'sdxl70': 'random-init SDXL UNet shapes, 128x128 latent, 77 tokens, all 70 cross-attn layers traced/step '
+                      '(mid block included)'}
     return f'{base[args.workload]}, {args.prompts} prompt(s)/GPU, {args.dtype}'
+
+
+def value_sets(layers, prompts):
+    set_bytes = algorithmic_bytes_per_step(layers, prompts) - px_per_step(layers, prompts) * 4   # accumulators once
+    return max(2, -(-int(320e6) // max(1, set_bytes))), set_bytes
+
+
+def shared_config(args, layers, world):
+    """The `config` object: identical for both arms of a run (the reference arm runs `on your arm's config`)."""
+    n_sets, set_bytes = value_sets(layers, args.prompts)
+    blocks = max(10, -(-200 // args.steps))
+    return {
+        'workload': workload_name(args), 'px_per_step': px_per_step(layers, args.prompts),
+        'px_definition': 'sum over traced layers of heads*77*h*w',
+        'literal_px_per_step': literal_px_per_step(layers, args.prompts),
+        'l2': f'inputs larger than L2: steps rotate over {n_sets} resident prompt sets '
+              f'({n_sets * set_bytes / 1e6:.0f} MB of accumulators+Q/K vs 126 MB L2), no flush',
+        'launch': 'one persistent kernel per step per pack of <= 32 traced layers',
+        'timing': f'value: median of {blocks} blocks of K={args.steps} steps (each block between barrier+synchronize, '
+                  f'CUDA events, max over ranks; launches queued behind a spin kernel so host pacing is not timed)',
+        'parallelism': f'prompts sharded, dp{world}',
+    }
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -466,15 +574,18 @@ def main():
     ap.add_argument('--steps', type=int, default=50)       # BASELINE configs[1]: 50 denoising steps
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='daam_b200', choices=['daam_b200', 'reference'])
-    ap.add_argument('--workload', default='sd21', choices=['sd21', 'sdxl', 'sd15'])
+    ap.add_argument('--workload', default='sd21', choices=['sd21', 'sdxl', 'sdxl70', 'sd15'])
     ap.add_argument('--prompts', type=int, default=1, help='prompts per GPU traced together (batch_prompts mode)')
     ap.add_argument('--dtype', default=None, choices=['bf16', 'fp16', 'fp32'])
+    ap.add_argument('--ref-device', default='cpu', choices=['cpu', 'cuda'],
+                    help='--impl reference only: where the reference hooks run (cpu = the contract\'s reference arm)')
     ap.add_argument('--skip-overhead', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-eager', action='store_true', help='skip the eager (no CUDA graph) e2e leg')
+    ap.add_argument('--skip-e2e', action='store_true', help='kernel legs only (profiling runs)')
     args = ap.parse_args()
-    if args.dtype is None:
-        args.dtype = {'sd21': 'bf16', 'sdxl': 'fp16', 'sd15': 'fp32'}[args.workload]   # sd15: the reference's default load
+    if args.dtype is None:   # sd15: the reference's default load
+        args.dtype = {'sd21': 'bf16', 'sdxl': 'fp16', 'sdxl70': 'fp16', 'sd15': 'fp32'}[args.workload]
     args.warmup = max(3, args.warmup)
     capture_stdout()
 
@@ -483,9 +594,8 @@ def main():
         return
 
     from daam_b200 import _native
-    from daam_b200.synthetic import SD15_SPEC, SD21_SPEC, SDXL_SPEC
     dtype = {'bf16': torch.bfloat16, 'fp16': torch.float16, 'fp32': torch.float32}[args.dtype]
-    spec = {'sd21': SD21_SPEC, 'sdxl': SDXL_SPEC, 'sd15': SD15_SPEC}[args.workload]
+    spec = workload_spec(args.workload)
     layers = traced_layers(args.workload)
     D = Dist(args.gpus)
     _native.load()
@@ -493,9 +603,14 @@ def main():
     windows = []
 
     with torch.no_grad():
-        ms, launches, n_sets = leg_value(args, layers, dtype, D, windows)
-        e2e_ms, h2d, d2h = leg_e2e(args, spec, dtype, D, windows, cuda_graph=True)
-        eager_ms = leg_e2e(args, spec, dtype, D, windows, cuda_graph=False)[0] if not args.skip_eager else float('nan')
+        ms, launches, n_sets, value_stats = leg_value(args, layers, dtype, D, windows)
+        e2e_ms = eager_ms = float('nan')
+        h2d = d2h = 0
+        order = None
+        if not args.skip_e2e:
+            e2e_ms, h2d, d2h, order = leg_e2e(args, spec, dtype, D, windows, cuda_graph=True)
+            if not args.skip_eager:
+                eager_ms = leg_e2e(args, spec, dtype, D, windows, cuda_graph=False)[0]
         overhead = None
         if not args.skip_overhead:       # every rank measures its own GPU (all ranks share the host's cores)
             try:
@@ -524,31 +639,44 @@ def main():
     bytes_step = algorithmic_bytes_per_step(layers, args.prompts, esize)
     peak, peak_src = measured_peak()
     achieved = bytes_step / (ms / args.steps * 1e-3) / 1e9        # GB/s per GPU (per-rank launch duration, max over ranks)
+    traffic = recorded_traffic(args.workload) if args.dtype == 'bf16' and args.prompts == 1 else None
+    e2e = None
+    if not args.skip_e2e:
+        e2e = {'value': px * args.steps * n / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps,
+               'eager_value': None if args.skip_eager else px * args.steps * n / (eager_ms * 1e-3),
+               'eager_ms_per_step': None if args.skip_eager else eager_ms / args.steps,
+               'what': 'with trace(pipe): pipe(prompt, K steps) on the cross-attn skeleton UNet (to_q/to_k/to_v, SDPA, '
+                       'to_out + fused heat-map kernel), pinned-host inputs H2D every step, + compute_global_heat_map '
+                       '(+ all_gather when N>1) + D2H of the maps; the pipeline replays the step from a CUDA graph '
+                       '(eager_*: same without graph replay, host-launch bound)'}
+        if order is not None:
+            e2e['gather_order_check'] = order
+        if overhead and 'hooked_ms_per_step' in overhead:
+            # the hook-overhead half of the metric, on the FULL-cost UNet (resnets, self-attention, feed-forward):
+            # un-hooked vs hooked forward, and the px/s a full-body generation sustains at that step time
+            worst = overhead.get('max_over_ranks', overhead)
+            e2e['hook_overhead'] = {
+                'unhooked_ms_per_step': worst['unhooked_ms_per_step'], 'hooked_ms_per_step': worst['hooked_ms_per_step'],
+                'overhead_ms_per_step': worst['overhead_ms_per_step'],
+                'overhead_pct': round(100 * worst['overhead_ms_per_step'] / worst['unhooked_ms_per_step'], 3),
+                'graph_overhead_pct': overhead.get('graph_overhead_pct'), 'ranks': n,
+                'full_body_value': px * n / (worst['hooked_ms_per_step'] * 1e-3), 'model': overhead.get('model')}
     line = {
         'metric': METRIC, 'value': px * args.steps * n / (ms * 1e-3), 'unit': UNIT, 'n_gpus': n, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
-        'config': {
-            'workload': workload_name(args), 'px_per_step': px, 'px_definition': 'sum over traced layers of heads*77*h*w',
-            'literal_px_per_step': literal_px_per_step(layers, args.prompts),
-            'l2': f'inputs larger than L2: steps rotate over {n_sets} resident prompt sets '
-                  f'({n_sets * (bytes_step - px * 4) / 1e6:.0f} MB of accumulators+Q/K vs 126 MB L2), no flush',
-            'launch': 'one persistent kernel per step covering all traced layers', 'parallelism': f'prompts sharded, dp{n}',
-        },
+        'config': shared_config(args, layers, n),
         'clocks': clocks,
-        'e2e': {'value': px * args.steps * n / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_ms / args.steps,
-                'eager_value': None if args.skip_eager else px * args.steps * n / (eager_ms * 1e-3),
-                'eager_ms_per_step': None if args.skip_eager else eager_ms / args.steps,
-                'what': 'with trace(pipe): pipe(prompt, K steps) on the cross-attn skeleton UNet (to_q/to_k/to_v, SDPA, '
-                        'to_out + fused heat-map kernel), pinned-host inputs H2D every step, + compute_global_heat_map '
-                        '(+ all_gather when N>1) + D2H of the maps; the pipeline replays the step from a CUDA graph '
-                        '(eager_*: same without graph replay, host-launch bound)'},
+        'e2e': e2e,
         'gpu_launches': launches,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                     'traffic': recorded_traffic(args.workload) if args.dtype == 'bf16' and args.prompts == 1 else None,
+                     'traffic': traffic.get('steady') if isinstance(traffic, dict) else traffic,
+                     'traffic_isolated_launch': traffic.get('isolated') if isinstance(traffic, dict) else None,
+                     'traffic_note': traffic.get('note') if isinstance(traffic, dict) else None,
                      'kernel': 'daam accumulate (softmax(QK^T)->unravel->+=)',
-                     'algorithmic_bytes_per_launch': bytes_step, 'peak_source': peak_src},
+                     'algorithmic_bytes_per_launch': bytes_step, 'peak_source': peak_src,
+                     'timing': value_stats},
         'cpu_baseline': cpu,
         'hook_overhead': overhead,
     }

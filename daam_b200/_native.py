@@ -17,6 +17,8 @@ DAAM_F32, DAAM_F16, DAAM_BF16 = 0, 1, 2
 ACC_AUTO, ACC_FORCE_SIMT, ACC_FORCE_MMA = 0, 1, 2
 ACC_RMW_AUTO, ACC_RMW_LDST, ACC_RMW_RED = 0x00, 0x10, 0x20
 ACC_NO_PDL = 0x100
+ACC_EARLY_LOADS = 0x200   # see include/daam_b200.h: only valid when q/k were complete before the previous kernel started
+ABI_VERSION = 3
 E_INVALID, E_UNSUPPORTED, E_CUDA = -1, -2, -3
 TOKENS = 77
 
@@ -63,6 +65,11 @@ def load() -> ctypes.CDLL:
             f'{LIB_PATH} is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
             f'(or `python -m daam_b200.build`). daam_b200 has no CPU fallback.')
     lib = ctypes.CDLL(LIB_PATH)
+    lib.daam_abi_version.argtypes = []
+    lib.daam_abi_version.restype = ctypes.c_int
+    if lib.daam_abi_version() != ABI_VERSION:
+        raise RuntimeError(f'{LIB_PATH} has ABI version {lib.daam_abi_version()}, this package needs {ABI_VERSION}: '
+                           f'rebuild it (`python -m daam_b200.build --force`)')
     i32, u32, i64, vp, f32 = ctypes.c_int32, ctypes.c_uint32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_float
     lib.daam_accumulate.argtypes = [ctypes.POINTER(DaamLayer), i32, u32, vp]
     lib.daam_accumulate.restype = ctypes.c_int

@@ -17,11 +17,13 @@
 // Persistent: every CTA walks a contiguous chunk of the launch's tiles; up to 2 CTAs per SM (256 TMEM columns each).
 //
 // fp32 projections (the reference's default dtype for SD-1.x/2.x, daam/run/generate.py:205) take the same kernel in
-// "split" form: tensor cores have no fp32 operand type and kind::tf32 would drop 13 mantissa bits, so four converter
-// warps load the fp32 Q/K tiles with coalesced 16-byte loads, split every value into three bf16 terms
-// (x = x1 + x2 + x3 carries all 24 significand bits), store them as three swizzled operand tiles each, and the MMA
-// warp accumulates the six products of order <= 2^-16 (q1k1 + q1k2 + q2k1 + q1k3 + q2k2 + q3k1) in fp32 in TMEM:
-// 24 MMAs per tile instead of 4, still far from the tensor pipe's limit, and the path stays HBM-bound.
+// "split" form. Tensor cores have no fp32 operand type and a plain kind::tf32 product would drop 13 mantissa bits, so
+// every value is used as two tf32 terms, x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi) (22 significand
+// bits, unbiased), and q.k = q_lo.k_hi + q_hi.k_lo + q_hi.k_hi (the dropped terms are <= 2^-22 relative): the fp32
+// Q/K tiles arrive by TMA exactly like the 16-bit ones (two 128-byte-wide swizzled sub-tiles per 64 dims), four
+// converter warps rewrite the landed tile in place to `hi` and emit `lo` into a second buffer (a shared-memory ->
+// shared-memory elementwise pass, swizzle-agnostic), and the MMA thread issues 3 x 8 tcgen05.mma kind::tf32 (K = 8)
+// per tile. One CTA per SM (two 52 KB raw stages + one lo buffer + the staged probabilities).
 //
 // head_dim other than 64 (SD-1.x: 40 / 80 / 160): the contraction runs in 64-wide K chunks, one chunk per smem stage,
 // accumulated into the same TMEM accumulator; the last chunk is zero-filled beyond head_dim (by the TMA unit, or by the
@@ -40,18 +42,21 @@ namespace daam {
 namespace {
 
 constexpr int kStages = 2;
-constexpr int kQBytes = kTilePixels * 128;            // 128 rows x 64 x 2 B
-constexpr int kKBytes = kTokensPad * 128;             // 80 rows x 64 x 2 B
+constexpr int kQBytes = kTilePixels * 128;            // 128 rows x 128 B (64 x 16-bit, or 32 x fp32: one swizzle span)
+constexpr int kKBytes = kTokensPad * 128;             // 80 rows x 128 B
 constexpr int kStageBytes = kQBytes + kKBytes;        // 26624 = 26 x 1024 (keeps every tile 1024-byte aligned)
 constexpr int kPBytes = kTokens * kTilePixels * 4;    // staged probabilities [77][128] fp32
 constexpr int kTmemCols = 256;
 constexpr int kAccCols = 128;                         // column distance between the two accumulators
 constexpr int kThreads = 192;
-constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kPBytes + 128;
-// split (fp32) form: a stage holds Q1 Q2 Q3 K1 K2 K3; warps 6-9 convert; one CTA per SM
-constexpr int kSplitStageBytes = 3 * kStageBytes;
-constexpr int kSplitThreads = 448;                 // + two converter groups of 4 warps, one per stage
-constexpr int kSplitSmemBytes = 1024 + kStages * kSplitStageBytes + kPBytes + 128;
+constexpr int kBarBytes = 256;                        // mbarriers + the TMEM base address slot
+constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kPBytes + kBarBytes;
+// split (fp32) form: a raw stage holds the fp32 tiles as [Q sub0][Q sub1][K sub0][K sub1] (sub-tile = 32 floats = one
+// 128-byte swizzle span per row); one more buffer of the same shape holds the lo terms; warps 6-9 convert
+constexpr int kSplitStageBytes = 2 * kStageBytes;     // 53248 = 52 x 1024
+constexpr int kSplitThreads = 320;
+constexpr int kSplitSmemBytes = 1024 + (kStages + 1) * kSplitStageBytes + kPBytes + kBarBytes;
+static_assert(kSplitSmemBytes <= 232448, "split form exceeds the 227 KB shared-memory limit");
 
 struct MmaParams {
   LaunchParams base;
@@ -141,6 +146,21 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::tf32: operands are 32-bit containers read as tf32, K = 8 per instruction (32 bytes along the swizzled row).
+__device__ __forceinline__ uint32_t umma_idesc_tf32() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTokensPad >> 3) << 17) | ((uint32_t)(kTilePixels >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -173,55 +193,27 @@ __device__ __forceinline__ Tile decode_tile(const LaunchParams& P, int tile, int
   return t;
 }
 
-// fp32 -> three bf16 terms, 8 values -> one 16-byte chunk per term
-__device__ __forceinline__ void split8(const float (&x)[8], uint4& p1, uint4& p2, uint4& p3) {
-  __nv_bfloat162 a[4], b[4], c[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float lo = x[2 * i], hi = x[2 * i + 1];
-    const __nv_bfloat16 a0 = __float2bfloat16_rn(lo), a1 = __float2bfloat16_rn(hi);
-    lo -= __bfloat162float(a0); hi -= __bfloat162float(a1);
-    const __nv_bfloat16 b0 = __float2bfloat16_rn(lo), b1 = __float2bfloat16_rn(hi);
-    lo -= __bfloat162float(b0); hi -= __bfloat162float(b1);
-    a[i] = __halves2bfloat162(a0, a1);
-    b[i] = __halves2bfloat162(b0, b1);
-    c[i] = __halves2bfloat162(__float2bfloat16_rn(lo), __float2bfloat16_rn(hi));
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// Converter warps (split form): a landed fp32 region [begin, end) of a raw stage (16-byte units, any swizzle -- the pass
+// is elementwise) is rewritten in place to hi = rna_tf32(x) and lo = rna_tf32(x - hi) goes to the same offsets of the lo
+// buffer. x - hi is exact in fp32 (|x - hi| <= half a tf32 ulp of x), so hi + lo carries 22 significand bits of x.
+__device__ __forceinline__ void split_region(uint8_t* raw, uint8_t* lo, int begin, int end, int ctid) {
+#pragma unroll 4
+  for (int off = begin + ctid * 16; off < end; off += 128 * 16) {
+    float4 x = *reinterpret_cast<const float4*>(raw + off);
+    float4 h, l;
+    h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
+    l.x = rna_tf32(x.x - h.x); l.y = rna_tf32(x.y - h.y); l.z = rna_tf32(x.z - h.z); l.w = rna_tf32(x.w - h.w);
+    *reinterpret_cast<float4*>(raw + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
   }
-  p1 = *reinterpret_cast<uint4*>(a);
-  p2 = *reinterpret_cast<uint4*>(b);
-  p3 = *reinterpret_cast<uint4*>(c);
 }
 
-// Converter warps (split form): rows [row0, row0 + n_rows_live) of a fp32 [rows x 64] operand -> three 128B-swizzled
-// K-major bf16 tiles at dst, dst + part_bytes, dst + 2 * part_bytes. 16-byte chunks of 8 floats, chunk = row * 8 +
-// group; rows >= n_rows_live and columns >= n_cols_live (a multiple of 8) are written as zeros. ctid: 0..127.
-template <int kChunksPerThread>
-__device__ __forceinline__ void convert_operand(const float* src_base, long long row_stride, int n_rows_live,
-                                                int n_cols_live, uint8_t* dst, int part_bytes, int ctid) {
-  float4 lo[kChunksPerThread], hi[kChunksPerThread];
-#pragma unroll
-  for (int c = 0; c < kChunksPerThread; ++c) {            // all loads first: 2 x kChunksPerThread in flight per thread
-    const int chunk = ctid + 128 * c, r = chunk >> 3, g = chunk & 7;
-    if (r < n_rows_live && g * 8 < n_cols_live) {
-      const float4* srcp = reinterpret_cast<const float4*>(src_base + (long long)r * row_stride + g * 8);
-      lo[c] = __ldg(srcp);
-      hi[c] = __ldg(srcp + 1);
-    } else {
-      lo[c] = hi[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < kChunksPerThread; ++c) {
-    const int chunk = ctid + 128 * c, r = chunk >> 3, g = chunk & 7;
-    const float x[8] = {lo[c].x, lo[c].y, lo[c].z, lo[c].w, hi[c].x, hi[c].y, hi[c].z, hi[c].w};
-    uint4 p1, p2, p3;
-    split8(x, p1, p2, p3);
-    const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((g ^ (r & 7)) << 4);     // SWIZZLE_128B, K-major
-    *reinterpret_cast<uint4*>(dst + off) = p1;
-    *reinterpret_cast<uint4*>(dst + part_bytes + off) = p2;
-    *reinterpret_cast<uint4*>(dst + 2 * part_bytes + off) = p3;
-  }
-}
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // kChunked: some layer of the launch has head_dim > 64 (several K chunks per tile); the common single-chunk case keeps
 // its simpler loops (one load iteration per tile).
@@ -229,16 +221,18 @@ template <bool kSplit, bool kChunked>
 __global__ void __launch_bounds__(kSplit ? kSplitThreads : kThreads, kSplit ? 1 : 2)
 accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
   constexpr int kStageBytesT = kSplit ? kSplitStageBytes : kStageBytes;
+  constexpr int kOperandBytes = (kSplit ? kStages + 1 : kStages) * kStageBytesT;     // stages (+ the lo buffer)
   const LaunchParams& P = MP.base;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                       // 1024-byte alignment for the swizzled tiles
   uint8_t* gen = smem_raw + (base - raw);
-  float* sP = reinterpret_cast<float*>(gen + kStages * kStageBytesT);
-  const uint32_t sP_u32 = base + kStages * kStageBytesT;
-  const uint32_t bars = sP_u32 + kPBytes;                             // 8 mbarriers + the TMEM base address
+  float* sP = reinterpret_cast<float*>(gen + kOperandBytes);
+  const uint32_t sP_u32 = base + kOperandBytes;
+  const uint32_t bars = sP_u32 + kPBytes;                             // 10 mbarriers + the TMEM base address
   const uint32_t full0 = bars, empty0 = bars + 16, tfull0 = bars + 32, tempty0 = bars + 48;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + kStages * kStageBytesT + kPBytes + 64);
+  const uint32_t lofull = bars + 64, loempty = bars + 72;             // split form: the lo buffer's hand-off
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + kOperandBytes + kPBytes + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = P.total_tiles / gridDim.x, rem = P.total_tiles % gridDim.x;
@@ -248,7 +242,7 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full0 + 8 * s, kSplit ? 128 : 1);   // split form: one arrival per converter thread
+      mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
 #pragma unroll
@@ -256,6 +250,8 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
       mbar_init(tfull0 + 8 * a, 1);
       mbar_init(tempty0 + 8 * a, 4);       // one arrival per epilogue warp
     }
+    mbar_init(lofull, 4);                  // one arrival per converter warp
+    mbar_init(loempty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) {
@@ -265,17 +261,14 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // descriptor fetches of the first tile overlap the barrier / TMEM set-up (and, under PDL, the previous kernel's tail)
-  // (not in the split form: it sits at the 128-register cap and any extra live state costs it ~15 %)
-  if constexpr (!kSplit) {
-    if (count > 0 && lane == 0 && (warp == 0 || warp == 4)) {
-      int li0 = 0;
-      const Tile t0 = decode_tile(P, first, li0);
-      if (warp == 0) {
-        prefetch_tensormap(&MP.amap[t0.li]);
-      } else {
-        prefetch_tensormap(&MP.qmap[t0.li]);
-        prefetch_tensormap(&MP.kmap[t0.li]);
-      }
+  if (count > 0 && lane == 0 && (warp == 0 || warp == 4)) {
+    int li0 = 0;
+    const Tile t0 = decode_tile(P, first, li0);
+    if (warp == 0) {
+      prefetch_tensormap(&MP.amap[t0.li]);
+    } else {
+      prefetch_tensormap(&MP.qmap[t0.li]);
+      prefetch_tensormap(&MP.kmap[t0.li]);
     }
   }
   tc_fence_before();
@@ -283,48 +276,38 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation) may overlap the tail of the
-  // previous kernel on the stream; nothing below (TMA loads, reduce-adds) may start before that kernel has completed
-  // and flushed. Our own dependents may be scheduled as soon as every CTA of this grid is past this point.
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  // previous kernel on the stream. By default nothing below starts before that kernel has completed and flushed.
+  // With `early_loads` (the caller vouches that Q/K were complete before the previous kernel started, DAAM_ACC_EARLY_LOADS)
+  // only the accumulator updates wait: loads, MMAs and the first tiles' softmax overlap the previous kernel's tail.
+  // Our own dependents may be scheduled as soon as every CTA of this grid is past this point.
+  if (!P.early_loads) griddep_wait();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (kSplit && warp >= 6) {
-    // ===== converter warps (fp32 projections): global fp32 -> three bf16 operand tiles per operand =====
-    // group g (warps 6-9 / 10-13) fills stage g with the load iterations j = g, g + 2, ... (one iteration = one 64-wide
-    // K chunk of one tile): two iterations' loads and conversions overlap
-    const int group = (warp - 6) >> 2;
-    const int ctid = (threadIdx.x - 192) & 127;
-    auto convert_chunk = [&](const Tile& t, const LayerParams& L, int c, uint32_t ph) {
-      mbar_wait(empty0 + 8 * group, ph ^ 1u);
-      uint8_t* stage = gen + group * kStageBytesT;
-      const int cols = min(64, L.head_dim - 64 * c);
-      const float* qsrc = static_cast<const float*>(L.q) + t.prompt * L.qs_prompt + t.head * L.qs_head +
-                          (long long)t.pixel0 * L.qs_pixel + 64 * c;
-      const float* ksrc = static_cast<const float*>(L.k) + t.prompt * L.ks_prompt + t.head * L.ks_head + 64 * c;
-      convert_operand<8>(qsrc, L.qs_pixel, min(kTilePixels, L.hw - t.pixel0), cols, stage, kQBytes, ctid);
-      convert_operand<5>(ksrc, L.ks_token, kTokens, cols, stage + 3 * kQBytes, kKBytes, ctid);
-      fence_proxy_async();                             // generic-proxy stores -> visible to the tensor core's reads
-      mbar_arrive(full0 + 8 * group);
-    };
-    int li = 0;
-    if constexpr (!kChunked) {
-      for (int i = group; i < count; i += kStages) {   // load iteration == tile
-        const Tile t = decode_tile(P, first + i, li);
-        convert_chunk(t, P.layer[t.li], 0, (uint32_t)(i >> 1) & 1u);
-      }
-    } else {
-      int j = 0;
-      for (int i = 0; i < count; ++i) {
-        const Tile t = decode_tile(P, first + i, li);
-        const LayerParams& L = P.layer[t.li];
-        const int n_chunks = (L.head_dim + 63) >> 6;
-        for (int c = 0; c < n_chunks; ++c, ++j)
-          if ((j & 1) == group) convert_chunk(t, L, c, (uint32_t)(j >> 1) & 1u);
+    // ===== converter warps (fp32 projections): landed fp32 tile -> hi (in place) + lo (second buffer) =====
+    const int ctid = threadIdx.x - 192;
+    uint8_t* lo = gen + kStages * kStageBytesT;
+    int li = 0, j = 0;
+    for (int i = 0; i < count; ++i) {
+      const Tile t = decode_tile(P, first + i, li);
+      const LayerParams& L = P.layer[t.li];
+      const int n_chunks = kChunked ? (L.head_dim + 63) >> 6 : 1;
+      for (int c = 0; c < n_chunks; ++c, ++j) {
+        const int s = j % kStages;
+        const int subs = (L.head_dim - 64 * c) > 32 ? 2 : 1;           // live 32-float sub-tiles of this chunk
+        mbar_wait(full0 + 8 * s, (uint32_t)(j / kStages) & 1u);         // TMA has landed the raw tiles
+        mbar_wait(loempty, ((uint32_t)j & 1u) ^ 1u);                   // the MMAs of the previous chunk have read lo
+        uint8_t* stage = gen + s * kStageBytesT;
+        split_region(stage, lo, 0, subs * kQBytes, ctid);
+        split_region(stage, lo, 2 * kQBytes, 2 * kQBytes + subs * kKBytes, ctid);
+        fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core's reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(lofull);
       }
     }
   } else if (warp == 4) {
-    // ===== TMA producer (16-bit projections) =====
-    if (!kSplit && lane == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
       int li = 0, j = 0;
       for (int i = 0; i < count; ++i) {
         const Tile t = decode_tile(P, first + i, li);
@@ -333,10 +316,23 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
           const int s = j % kStages;
           const uint32_t ph = (uint32_t)(j / kStages) & 1u;
           mbar_wait(empty0 + 8 * s, ph ^ 1u);
-          mbar_expect_tx(full0 + 8 * s, kStageBytes);
-          const uint32_t q_dst = base + s * kStageBytesT, k_dst = q_dst + kQBytes;
-          tma_load_4d(&MP.qmap[t.li], full0 + 8 * s, q_dst, 64 * c, t.head, t.pixel0, t.prompt);
-          tma_load_4d(&MP.kmap[t.li], full0 + 8 * s, k_dst, 64 * c, t.head, 0, t.prompt);
+          const uint32_t q_dst = base + s * kStageBytesT;
+          if constexpr (kSplit) {                      // fp32: up to two 32-float-wide boxes per operand
+            const bool two = (P.layer[t.li].head_dim - 64 * c) > 32;    // the second sub-tile has live columns
+            const uint32_t k_dst = q_dst + 2 * kQBytes;
+            mbar_expect_tx(full0 + 8 * s, two ? kStageBytesT : kStageBytes);
+            tma_load_4d(&MP.qmap[t.li], full0 + 8 * s, q_dst, 64 * c, t.head, t.pixel0, t.prompt);
+            tma_load_4d(&MP.kmap[t.li], full0 + 8 * s, k_dst, 64 * c, t.head, 0, t.prompt);
+            if (two) {
+              tma_load_4d(&MP.qmap[t.li], full0 + 8 * s, q_dst + kQBytes, 64 * c + 32, t.head, t.pixel0, t.prompt);
+              tma_load_4d(&MP.kmap[t.li], full0 + 8 * s, k_dst + kKBytes, 64 * c + 32, t.head, 0, t.prompt);
+            }
+          } else {
+            const uint32_t k_dst = q_dst + kQBytes;
+            mbar_expect_tx(full0 + 8 * s, kStageBytes);
+            tma_load_4d(&MP.qmap[t.li], full0 + 8 * s, q_dst, 64 * c, t.head, t.pixel0, t.prompt);
+            tma_load_4d(&MP.kmap[t.li], full0 + 8 * s, k_dst, 64 * c, t.head, 0, t.prompt);
+          }
         }
       }
     }
@@ -355,23 +351,28 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
         for (int c = 0; c < n_chunks; ++c, ++j) {
           const int s = j % kStages;
           const uint32_t ph = (uint32_t)(j / kStages) & 1u;
-          mbar_wait(full0 + 8 * s, ph);                // the chunk's operand tiles have landed
-          tc_fence_after();
           const uint32_t q_src = base + s * kStageBytesT;
-          const int k_steps = (min(64, L.head_dim - 64 * c) + 15) >> 4;   // UMMA_K 16 = 32 bytes along the swizzled row
+          const int cols = min(64, L.head_dim - 64 * c);
           if constexpr (kSplit) {
-            // q.k = sum of the six split products up to order 2^-16, smallest first; every operand is bf16
-            const uint32_t k_src = q_src + 3 * kQBytes;
-            const uint32_t idesc = umma_idesc(true);
-            constexpr int qa[6] = {2, 0, 1, 1, 0, 0}, kb[6] = {0, 2, 1, 0, 1, 0};
+            mbar_wait(lofull, (uint32_t)j & 1u);       // hi (in place) and lo are written (implies the TMA has landed)
+            tc_fence_after();
+            // q.k = q_lo.k_hi + q_hi.k_lo + q_hi.k_hi, smallest first; K = 8 floats = 32 bytes per instruction
+            const int k_steps = (cols + 7) >> 3;
+            const uint32_t q_lo = base + kStages * kStageBytesT, idesc = umma_idesc_tf32();
+            const uint32_t qa[3] = {q_lo, q_src, q_src};
+            const uint32_t kb[3] = {q_src + 2 * kQBytes, q_lo + 2 * kQBytes, q_src + 2 * kQBytes};
 #pragma unroll
-            for (int p = 0; p < 6; ++p)
+            for (int p = 0; p < 3; ++p)
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
+              for (int k = 0; k < 8; ++k)
                 if (k < k_steps)
-                  umma_f16(d_tmem, umma_desc_sw128(q_src + qa[p] * kQBytes + 32 * k),
-                           umma_desc_sw128(k_src + kb[p] * kKBytes + 32 * k), idesc, (c | p | k) != 0);
+                  umma_tf32(d_tmem, umma_desc_sw128(qa[p] + (k >> 2) * kQBytes + 32 * (k & 3)),
+                            umma_desc_sw128(kb[p] + (k >> 2) * kKBytes + 32 * (k & 3)), idesc, (c | p | k) != 0);
+            umma_commit(loempty);                      // frees the lo buffer ...
           } else {
+            mbar_wait(full0 + 8 * s, ph);              // the chunk's operand tiles have landed
+            tc_fence_after();
+            const int k_steps = (cols + 15) >> 4;      // UMMA_K 16 = 32 bytes along the swizzled row
             const uint32_t k_src = q_src + kQBytes;
             const uint32_t idesc = umma_idesc(L.dtype == DAAM_BF16);
 #pragma unroll
@@ -379,7 +380,7 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
               if (k < k_steps)
                 umma_f16(d_tmem, umma_desc_sw128(q_src + 32 * k), umma_desc_sw128(k_src + 32 * k), idesc, (c | k) != 0);
           }
-          umma_commit(empty0 + 8 * s);                 // frees the smem stage once the MMAs have read it
+          umma_commit(empty0 + 8 * s);                 // ... and the smem stage once the MMAs have read them
         }
         umma_commit(tfull0 + 8 * a);                   // accumulator ready for the epilogue
       }
@@ -416,6 +417,8 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
         sum += v[j];
       }
       const float inv = 1.0f / sum;
+      // the first accumulator update of this CTA: everything the previous kernel added must be complete and visible
+      if (i == 0 && P.early_loads) griddep_wait();
 
       if (P.rmw_mode == 1) {
         if (tid == 0 && issued) bulk_wait_read0();     // the previous reduce has finished reading sP
@@ -446,7 +449,8 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
         }
       }
     }
-    if (tid == 0 && issued) bulk_wait0();
+    // shared memory must outlive the reduce's reads; its global writes complete with the grid (same rule as a TMA store)
+    if (tid == 0 && issued) bulk_wait_read0();
   }
 
   tc_fence_before();
@@ -501,8 +505,8 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash>& map_cache() {
 }
 std::mutex g_map_mu;
 
-// {head_dim, heads, rows, prompts} view of a projection; box = [box_rows x 64 dims] of one head, 128B-swizzled (columns
-// beyond head_dim in the last K chunk are zero-filled).
+// {head_dim, heads, rows, prompts} view of a projection; box = [box_rows x one 128-byte swizzle span] of one head (64
+// 16-bit or 32 fp32 dims), 128B-swizzled; columns beyond head_dim are zero-filled.
 int make_qk_map(const void* ptr, int dtype, int head_dim, int heads, int rows, int prompts, long long s_head,
                 long long s_row, long long s_prompt, int box_rows, CUtensorMap* out) {
   MapKey key{ptr, s_head, s_row, s_prompt, heads, rows, prompts * 1024 + box_rows, (dtype << 4) | (head_dim << 8)};
@@ -513,13 +517,16 @@ int make_qk_map(const void* ptr, int dtype, int head_dim, int heads, int rows, i
   }
   EncodeFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DAAM_E_CUDA; }
+  const cuuint64_t es = dtype == DAAM_F32 ? 4 : 2;
   const cuuint64_t dims[4] = {(cuuint64_t)head_dim, (cuuint64_t)heads, (cuuint64_t)rows, (cuuint64_t)prompts};
-  auto bytes = [](long long s) { return (cuuint64_t)(s > 0 ? s : 8) * 2; };
+  auto bytes = [es](long long s) { return (cuuint64_t)(s > 0 ? s : 8) * es; };
   const cuuint64_t strides[3] = {bytes(s_head), bytes(s_row), bytes(s_prompt)};
-  const cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)(128 / es), 1, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(out, dtype == DAAM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
-                   const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const CUtensorMapDataType type = dtype == DAAM_F32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                   : dtype == DAAM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                        : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(out, type, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(q/k) failed with CUresult %d", (int)r); return DAAM_E_CUDA; }
   std::lock_guard<std::mutex> lock(g_map_mu);
@@ -552,57 +559,79 @@ int make_acc_map(float* acc, int hw, int rows, CUtensorMap* out) {
   return DAAM_OK;
 }
 
+std::once_flag g_attr_once[64];                       // the shared-memory attribute is per device
+
 }  // namespace
 
+// Parameter block of one tcgen05 launch, opaque to api.cu (which caches prepared launches by their daam_layer[] input).
+struct PreparedMma {
+  MmaParams mp;
+  int grid, block, smem, variant;                     // variant: bit 0 split (fp32), bit 1 chunked (head_dim > 64)
+};
+size_t prepared_mma_size() { return sizeof(PreparedMma); }
+
 bool mma_supported(const LayerParams& L) {
-  return L.head_dim % 8 == 0 && L.head_dim <= 192 && L.vec_ok && L.qs_head > 0 && L.qs_pixel > 0 && L.ks_head > 0 &&
-         L.ks_token > 0;
+  return L.head_dim % 8 == 0 && L.head_dim <= DAAM_MAX_HEAD_DIM && L.vec_ok && L.qs_head > 0 && L.qs_pixel > 0 &&
+         L.ks_head > 0 && L.ks_token > 0;
 }
 
-int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStream_t stream) {
+// Tensor maps, grid and kernel variant of one pack of layers (all fp32, or all 16-bit). `out` points at
+// prepared_mma_size() bytes owned by the caller.
+int prepare_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, void* out) {
   if (dev.cc_major != 10) { set_error("the tcgen05 kernel needs an sm_100 device (found sm_%d%d)", dev.cc_major, dev.cc_minor); return DAAM_E_UNSUPPORTED; }
-  static thread_local MmaParams mp;
+  PreparedMma& pm = *static_cast<PreparedMma*>(out);
+  MmaParams& mp = pm.mp;
   mp.base = p;
   const bool split = p.n_layers > 0 && p.layer[0].dtype == DAAM_F32;     // a pack holds one operand class (api.cu)
+  bool chunked = false;
   for (int i = 0; i < p.n_layers; ++i) {
     const LayerParams& L = p.layer[i];
     if ((L.dtype == DAAM_F32) != split) { set_error("mixed fp32 / 16-bit layers in one tcgen05 pack"); return DAAM_E_INVALID; }
-    if (!split) {
-      if (int rc = make_qk_map(L.q, L.dtype, L.head_dim, L.heads, L.hw, L.n_prompts, L.qs_head, L.qs_pixel, L.qs_prompt, kTilePixels, &mp.qmap[i])) return rc;
-      if (int rc = make_qk_map(L.k, L.dtype, L.head_dim, L.heads, kTokens, L.n_prompts, L.ks_head, L.ks_token, L.ks_prompt, kTokensPad, &mp.kmap[i])) return rc;
-    }
+    if (int rc = make_qk_map(L.q, L.dtype, L.head_dim, L.heads, L.hw, L.n_prompts, L.qs_head, L.qs_pixel, L.qs_prompt, kTilePixels, &mp.qmap[i])) return rc;
+    if (int rc = make_qk_map(L.k, L.dtype, L.head_dim, L.heads, kTokens, L.n_prompts, L.ks_head, L.ks_token, L.ks_prompt, kTokensPad, &mp.kmap[i])) return rc;
     if (int rc = make_acc_map(L.acc, L.hw, L.n_prompts * L.heads * kTokens, &mp.amap[i])) return rc;
+    chunked = chunked || L.head_dim > 64;
   }
-  static bool configured_dev[64] = {};                // the attribute is per device
-  bool& configured = configured_dev[dev.device & 63];
-  if (!configured) {
-    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmemBytes));
-    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_mma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSplitSmemBytes));
-    configured = true;
-  }
-  int grid = dev.sm_count * (split ? 1 : 2);
-  if (grid > p.total_tiles) grid = p.total_tiles;
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(g_attr_once[dev.device & 63], [&] {
+    auto set = [&](const void* fn, int bytes) {
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e != cudaSuccess) attr_err = e;
+    };
+    set((const void*)accumulate_mma_kernel<false, false>, kSmemBytes);
+    set((const void*)accumulate_mma_kernel<false, true>, kSmemBytes);
+    set((const void*)accumulate_mma_kernel<true, false>, kSplitSmemBytes);
+    set((const void*)accumulate_mma_kernel<true, true>, kSplitSmemBytes);
+  });
+  DAAM_CUDA_TRY(attr_err);
+  pm.grid = dev.sm_count * (split ? 1 : 2);
+  if (pm.grid > p.total_tiles) pm.grid = p.total_tiles;
+  pm.block = split ? kSplitThreads : kThreads;
+  pm.smem = split ? kSplitSmemBytes : kSmemBytes;
+  pm.variant = (split ? 1 : 0) | (chunked ? 2 : 0);
+  return DAAM_OK;
+}
+
+int launch_prepared_mma(const void* prepared, cudaStream_t stream) {
+  const PreparedMma& pm = *static_cast<const PreparedMma*>(prepared);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(split ? kSplitThreads : kThreads);
-  cfg.dynamicSmemBytes = split ? kSplitSmemBytes : kSmemBytes;
+  cfg.gridDim = dim3(pm.grid);
+  cfg.blockDim = dim3(pm.block);
+  cfg.dynamicSmemBytes = pm.smem;
   cfg.stream = stream;
-  // Inside a stream capture the launch becomes a plain kernel node (programmatic edges are left to the graph owner).
-  cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
-  DAAM_CUDA_TRY(cudaStreamIsCapturing(stream, &capture));
+  // Programmatic stream serialization also inside a stream capture: the launch becomes a kernel node with a programmatic
+  // edge from its predecessor (CUDA >= 12.3).
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = (p.pdl && capture == cudaStreamCaptureStatusNone) ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = pm.mp.base.pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  bool chunked = false;
-  for (int i = 0; i < p.n_layers; ++i) chunked = chunked || p.layer[i].head_dim > 64;
-  if (split && chunked) DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<true, true>, mp));
-  else if (split) DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<true, false>, mp));
-  else if (chunked) DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<false, true>, mp));
-  else DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<false, false>, mp));
+  switch (pm.variant) {
+    case 0: DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<false, false>, pm.mp)); break;
+    case 1: DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<true, false>, pm.mp)); break;
+    case 2: DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<false, true>, pm.mp)); break;
+    default: DAAM_CUDA_TRY(cudaLaunchKernelEx(&cfg, accumulate_mma_kernel<true, true>, pm.mp)); break;
+  }
   DAAM_CUDA_TRY(cudaGetLastError());
   count_launch();
   return DAAM_OK;

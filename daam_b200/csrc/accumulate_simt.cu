@@ -5,6 +5,8 @@
 // logits live in registers, K^T sits in shared memory and is read as warp-wide broadcasts, so softmax needs no
 // shuffles and the accumulator update `acc[t][pixel] += p[t]` is one fully coalesced 128-byte access per warp and
 // token. Replaces daam/trace.py:276 (get_attention_scores), :219-244 (_unravel_attn) and :293-294 (update loop).
+#include <mutex>
+
 #include "simt_common.cuh"
 
 namespace daam {
@@ -57,22 +59,32 @@ __global__ void __launch_bounds__(kTilePixels, 3) accumulate_simt_kernel(const _
 
 }  // namespace
 
-int launch_accumulate_simt(const LaunchParams& p, const DeviceInfo& dev, cudaStream_t stream) {
+int prepare_accumulate_simt(const LaunchParams& p, const DeviceInfo& dev, int* grid_out, size_t* smem_out) {
   int dmax = 0;
   for (int i = 0; i < p.n_layers; ++i) dmax = p.layer[i].head_dim > dmax ? p.layer[i].head_dim : dmax;
   const size_t smem = sizeof(float) * simt::tile_smem_floats(dmax);
+  static std::mutex mu;
   static size_t configured_dev[64] = {};              // the attribute is per device
-  size_t& configured = configured_dev[dev.device & 63];
-  if (smem > configured) {
-    DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-    configured = smem;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& configured = configured_dev[dev.device & 63];
+    if (smem > configured) {
+      DAAM_CUDA_TRY(cudaFuncSetAttribute(accumulate_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+      configured = smem;
+    }
   }
   int occ = 0;
   DAAM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, accumulate_simt_kernel, kTilePixels, smem));
   if (occ < 1) occ = 1;
   int grid = dev.sm_count * occ;
   if (grid > p.total_tiles) grid = p.total_tiles;
+  *grid_out = grid;
+  *smem_out = smem;
+  return DAAM_OK;
+}
+
+int launch_prepared_simt(const LaunchParams& p, int grid, size_t smem, cudaStream_t stream) {
   accumulate_simt_kernel<<<grid, kTilePixels, smem, stream>>>(p);
   DAAM_CUDA_TRY(cudaGetLastError());
   count_launch();

@@ -4,7 +4,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -81,24 +83,56 @@ int make_layer_params(const daam_layer& in, int index, LayerParams* out, bool ne
 
 using namespace daam;
 
-extern "C" int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint32_t flags, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (n_layers < 0 || (n_layers > 0 && !layers)) { set_error("daam_accumulate: bad layer array"); return DAAM_E_INVALID; }
-  if (n_layers == 0) return DAAM_OK;
-  DeviceInfo dev;
-  if (int rc = get_device_info(&dev)) return rc;
-  const uint32_t path = flags & 3u, rmw = flags & DAAM_ACC_RMW_MASK;
+namespace daam {
+namespace {
 
+// One kernel launch of a plan: a pack of layers for the tcgen05 kernel (prepared block, opaque) or the SIMT kernel.
+struct PlannedLaunch {
+  bool is_mma = false;
+  LaunchParams simt;                     // SIMT: the parameter block itself
+  int grid = 0;
+  size_t smem = 0;
+  std::unique_ptr<uint8_t[]> mma;        // tcgen05: PreparedMma (tensor maps + parameter block)
+};
+
+// Everything daam_accumulate derives from its input: the packs, their tensor maps, grids. A trace replays the same
+// layer calls (same pointers: the caching allocator hands the projections the same addresses) every denoising step,
+// so plans are cached by the verbatim daam_layer[] input; a hit costs one memcmp instead of ~3 hash lookups per layer.
+struct Plan {
+  std::vector<uint8_t> key;              // the caller's daam_layer[n] bytes
+  uint32_t flags = 0;
+  int device = -1;
+  std::vector<PlannedLaunch> launches;
+  uint64_t stamp = 0;
+};
+constexpr size_t kMaxPlans = 32;
+
+int build_plan(const daam_layer* layers, int n_layers, uint32_t flags, const DeviceInfo& dev, Plan* plan) {
+  const uint32_t path = flags & 3u, rmw = flags & DAAM_ACC_RMW_MASK;
   // Three packs: 16-bit layers for the tcgen05 kernel (TMA form), fp32 layers for its split form, and the rest for
-  // the SIMT kernel. Each is flushed when its parameter block is full.
-  static thread_local LaunchParams mma, mma32, simt;
-  mma.n_layers = mma32.n_layers = simt.n_layers = 0;
-  mma.total_tiles = mma32.total_tiles = simt.total_tiles = 0;
-  mma.rmw_mode = mma32.rmw_mode = simt.rmw_mode = (rmw == DAAM_ACC_RMW_LDST) ? 0 : 1;   // default: reduce-add
-  mma.pdl = mma32.pdl = simt.pdl = (flags & DAAM_ACC_NO_PDL) ? 0 : 1;
-  auto flush = [&](LaunchParams& p, bool is_mma) -> int {
+  // the SIMT kernel. Each is closed when its parameter block is full.
+  LaunchParams packs[3];                 // 0: tcgen05 16-bit, 1: tcgen05 fp32, 2: SIMT
+  for (LaunchParams& p : packs) {
+    p.n_layers = p.total_tiles = 0;
+    p.rmw_mode = (rmw == DAAM_ACC_RMW_LDST) ? 0 : 1;     // default: reduce-add
+    p.pdl = (flags & DAAM_ACC_NO_PDL) ? 0 : 1;
+    p.early_loads = (flags & DAAM_ACC_EARLY_LOADS) && p.pdl ? 1 : 0;
+    p.pad_ = 0;
+  }
+  auto close = [&](int which) -> int {
+    LaunchParams& p = packs[which];
     if (p.n_layers == 0) return DAAM_OK;
-    int rc = is_mma ? launch_accumulate_mma(p, dev, stream) : launch_accumulate_simt(p, dev, stream);
+    plan->launches.emplace_back();
+    PlannedLaunch& l = plan->launches.back();
+    l.is_mma = which != 2;
+    int rc;
+    if (l.is_mma) {
+      l.mma.reset(new uint8_t[prepared_mma_size()]);
+      rc = prepare_accumulate_mma(p, dev, l.mma.get());
+    } else {
+      l.simt = p;
+      rc = prepare_accumulate_simt(p, dev, &l.grid, &l.smem);
+    }
     p.n_layers = 0;
     p.total_tiles = 0;
     return rc;
@@ -106,22 +140,66 @@ extern "C" int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint3
   for (int i = 0; i < n_layers; ++i) {
     LayerParams L;
     if (int rc = make_layer_params(layers[i], i, &L, /*need_acc=*/true)) return rc;
-    bool use_mma = path != DAAM_ACC_FORCE_SIMT && mma_supported(L);
+    const bool use_mma = path != DAAM_ACC_FORCE_SIMT && dev.cc_major == 10 && mma_supported(L);
     if (path == DAAM_ACC_FORCE_MMA && !use_mma) {
-      set_error("daam_accumulate: layer %d cannot take the tcgen05 path (dtype %d, head_dim %d, alignment %d)", i,
-                L.dtype, L.head_dim, L.vec_ok);
+      set_error("daam_accumulate: layer %d cannot take the tcgen05 path (dtype %d, head_dim %d, alignment %d, sm_%d%d)", i,
+                L.dtype, L.head_dim, L.vec_ok, dev.cc_major, dev.cc_minor);
       return DAAM_E_UNSUPPORTED;
     }
-    LaunchParams& p = use_mma ? (L.dtype == DAAM_F32 ? mma32 : mma) : simt;
+    const int which = use_mma ? (L.dtype == DAAM_F32 ? 1 : 0) : 2;
+    LaunchParams& p = packs[which];
     L.tile_begin = p.total_tiles;
     p.layer[p.n_layers++] = L;
     p.total_tiles += L.tiles_per_head * L.heads * L.n_prompts;
     if (p.n_layers == kMaxLayersPerLaunch)
-      if (int rc = flush(p, use_mma)) return rc;
+      if (int rc = close(which)) return rc;
   }
-  if (int rc = flush(mma, true)) return rc;
-  if (int rc = flush(mma32, true)) return rc;
-  if (int rc = flush(simt, false)) return rc;
+  for (int which = 0; which < 3; ++which)
+    if (int rc = close(which)) return rc;
+  return DAAM_OK;
+}
+
+}  // namespace
+}  // namespace daam
+
+extern "C" int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint32_t flags, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_layers < 0 || (n_layers > 0 && !layers)) { set_error("daam_accumulate: bad layer array"); return DAAM_E_INVALID; }
+  if (n_layers == 0) return DAAM_OK;
+  DeviceInfo dev;
+  if (int rc = get_device_info(&dev)) return rc;
+
+  static thread_local std::vector<std::unique_ptr<Plan>> plans;    // per calling thread: no locking on the hot path
+  static thread_local uint64_t clock = 0;
+  const size_t bytes = sizeof(daam_layer) * (size_t)n_layers;
+  Plan* plan = nullptr;
+  for (auto& c : plans)
+    if (c->key.size() == bytes && c->flags == flags && c->device == dev.device && memcmp(c->key.data(), layers, bytes) == 0) {
+      plan = c.get();
+      break;
+    }
+  if (!plan) {
+    std::unique_ptr<Plan> fresh(new Plan);
+    fresh->key.assign(reinterpret_cast<const uint8_t*>(layers), reinterpret_cast<const uint8_t*>(layers) + bytes);
+    fresh->flags = flags;
+    fresh->device = dev.device;
+    if (int rc = build_plan(layers, n_layers, flags, dev, fresh.get())) return rc;     // failed plans are not cached
+    if (plans.size() >= kMaxPlans) {                                                   // evict the least recently used
+      size_t oldest = 0;
+      for (size_t i = 1; i < plans.size(); ++i)
+        if (plans[i]->stamp < plans[oldest]->stamp) oldest = i;
+      plans[oldest] = std::move(fresh);
+      plan = plans[oldest].get();
+    } else {
+      plans.push_back(std::move(fresh));
+      plan = plans.back().get();
+    }
+  }
+  plan->stamp = ++clock;
+  for (const PlannedLaunch& l : plan->launches) {
+    const int rc = l.is_mma ? launch_prepared_mma(l.mma.get(), stream) : launch_prepared_simt(l.simt, l.grid, l.smem, stream);
+    if (rc) return rc;
+  }
   return DAAM_OK;
 }
 

@@ -36,6 +36,8 @@ struct LaunchParams {
   int total_tiles;
   int rmw_mode;             // 0: load/add/store, 1: reduce-add
   int pdl;                  // 1: launch with programmatic stream serialization (prologue overlaps the previous kernel)
+  int early_loads;          // 1: only the accumulator updates wait for the previous kernel (DAAM_ACC_EARLY_LOADS)
+  int pad_;
   LayerParams layer[kMaxLayersPerLaunch];
 };
 
@@ -64,8 +66,13 @@ int get_device_info(DeviceInfo* out);   // cached per device
 void count_launch(int n = 1);
 
 // ---- kernel launchers (one per translation unit) ----------------------------------------------------------------
-int launch_accumulate_simt(const LaunchParams& p, const DeviceInfo& dev, cudaStream_t stream);
-int launch_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, cudaStream_t stream);
+// Preparation (tensor maps, grid, shared-memory size) is split from the launch so that api.cu can cache it per
+// distinct daam_layer[] input: the steady state of a trace replays the same layer calls every denoising step.
+int prepare_accumulate_simt(const LaunchParams& p, const DeviceInfo& dev, int* grid, size_t* smem);
+int launch_prepared_simt(const LaunchParams& p, int grid, size_t smem, cudaStream_t stream);
+size_t prepared_mma_size();
+int prepare_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, void* prepared);
+int launch_prepared_mma(const void* prepared, cudaStream_t stream);
 bool mma_supported(const LayerParams& l);
 
 }  // namespace daam

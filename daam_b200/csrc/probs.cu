@@ -6,6 +6,8 @@
 //    accumulate_simt.cu; the 128 x 77 block of a tile is contiguous in P and written out coalesced through shared memory.
 //  * accumulate_probs_kernel -- heat-map accumulation from supplied probabilities (load_heads, trace.py:281-294):
 //    acc[r][token][pixel] += P[first_row + r][pixel][token]  (= _unravel_attn + update).
+#include <mutex>
+
 #include "simt_common.cuh"
 
 namespace daam {
@@ -107,15 +109,20 @@ extern "C" int daam_attention_probs(const daam_layer* layer, void* probs, void* 
   p.total_tiles = p.layer[0].tiles_per_head * p.layer[0].heads * p.layer[0].n_prompts;
   p.rmw_mode = 0;
   p.pdl = 0;
+  p.early_loads = 0;
   size_t floats = simt::tile_smem_floats(p.layer[0].head_dim);
   const size_t need = (size_t)p.layer[0].head_dim * kTokensPad + (size_t)kTilePixels * kTokens;   // K^T + staged P
   if (need > floats) floats = need;
   const size_t smem = floats * sizeof(float);
+  static std::mutex mu;
   static size_t configured_dev[64] = {};              // the attribute is per device
-  size_t& configured = configured_dev[dev.device & 63];
-  if (smem > configured) {
-    DAAM_CUDA_TRY(cudaFuncSetAttribute(attention_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& configured = configured_dev[dev.device & 63];
+    if (smem > configured) {
+      DAAM_CUDA_TRY(cudaFuncSetAttribute(attention_probs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
   }
   int grid = dev.sm_count * 3;
   if (grid > p.total_tiles) grid = p.total_tiles;

@@ -31,7 +31,7 @@ import torch.nn.functional as F
 
 __all__ = [
     'SyntheticAttention', 'SDPAProcessor', 'SyntheticUNet', 'SyntheticPipeline', 'WhitespaceTokenizer',
-    'UNetSpec', 'SD21_SPEC', 'SDXL_SPEC', 'SD15_SPEC', 'TINY_SPEC', 'TINY15_SPEC', 'make_pipeline',
+    'UNetSpec', 'SD21_SPEC', 'SDXL_SPEC', 'SD15_SPEC', 'TINY_SPEC', 'TINY15_SPEC', 'TINY96_SPEC', 'make_pipeline',
 ]
 
 
@@ -313,6 +313,9 @@ SD15_SPEC = UNetSpec('sd15', 64, (320, 640, 1280, 1280), (8, 8, 8, 8), (1, 1, 1,
 TINY_SPEC = UNetSpec('tiny', 64, (64, 128, 128, 128), (1, 2, 2, 2), (1, 1, 1, 0), 96)
 # the same topology with SD-1.x style head dims (40 / 80 / 80)
 TINY15_SPEC = UNetSpec('tiny15', 64, (80, 160, 160, 160), (2, 2, 2, 2), (1, 1, 1, 0), 96, dim_head=None)
+# the 768-pixel models' geometry (96x96 latent -> latent_hw 9216, daam/trace.py:32-33): layers at 96^2 / 48^2 / 24^2
+# (9216 / 2304 / 576 query positions: partial 128-pixel tiles), mid layer at 12^2 (factor 8, skipped)
+TINY96_SPEC = UNetSpec('tiny96', 96, (64, 128, 128, 128), (1, 2, 2, 2), (1, 1, 1, 0), 96)
 
 
 class SyntheticUNet(nn.Module):

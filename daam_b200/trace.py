@@ -191,13 +191,16 @@ class DiffusionHeatMapHooker(AggregateHooker):
         packed.n = n
         if torch.cuda.is_current_stream_capturing():
             # CUDA-graph capture of the UNet step: the launch becomes a node of the captured stream itself
+            # (its predecessor on that stream is the tail of the UNet forward, never a producer of the queued Q/K)
             for item in pending:
                 item[4].captured = True
-            ops.accumulate(packed, device, flags=self.kernel_flags)
+            ops.accumulate(packed, device, flags=self.kernel_flags | _native.ACC_EARLY_LOADS)
         else:
             side = self._side_stream(device)
             side.wait_stream(torch.cuda.current_stream(device))   # Q/K were produced on the current stream
-            ops.accumulate(packed, device, stream=side, flags=self.kernel_flags)
+            # the side stream carries nothing but these launches: the projections are complete (event above) before the
+            # previous launch could have started, so only the accumulator updates need to wait for it (EARLY_LOADS)
+            ops.accumulate(packed, device, stream=side, flags=self.kernel_flags | _native.ACC_EARLY_LOADS)
             # Keep the projections alive until the kernel has run: park the references behind an event instead of
             # 2 x n_layers record_stream calls; batches whose event has fired are dropped here, one step later.
             done = torch.cuda.Event()

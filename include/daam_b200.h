@@ -24,9 +24,10 @@
 extern "C" {
 #endif
 
-#define DAAM_ABI_VERSION 2          /* 2: + daam_attention_probs, daam_accumulate_probs, daam_finalize_per_key */
+#define DAAM_ABI_VERSION 3          /* 2: + daam_attention_probs, daam_accumulate_probs, daam_finalize_per_key
+                                       3: + DAAM_ACC_EARLY_LOADS, daam_expand_words */
 #define DAAM_TOKENS 77          /* context length the reference traces (daam/trace.py:194, guard at :289) */
-#define DAAM_MAX_HEAD_DIM 160   /* SD-1.x deepest level: 1280 channels / 8 heads */
+#define DAAM_MAX_HEAD_DIM 256   /* any multiple of 8 up to here (SD-1.x deepest level: 1280 channels / 8 heads = 160) */
 
 enum daam_status {
   DAAM_OK = 0,
@@ -48,6 +49,13 @@ enum daam_dtype { DAAM_F32 = 0, DAAM_F16 = 1, DAAM_BF16 = 2 };
 #define DAAM_ACC_RMW_LDST   0x10u /* coalesced load / add / store of the accumulator tile */
 #define DAAM_ACC_RMW_RED    0x20u /* red.global.add.f32 (SIMT) / bulk-async reduce-add from shared memory (MMA) */
 #define DAAM_ACC_NO_PDL     0x100u /* launch without programmatic dependent launch (measurement / debugging) */
+#define DAAM_ACC_EARLY_LOADS 0x200u /* The caller vouches that q and k of every layer were complete BEFORE the previous
+                                     kernel on `stream` started (they were produced on another stream and joined through
+                                     an event, or are resident inputs). Then only the kernel's accumulator updates wait
+                                     for the previous kernel (programmatic dependent launch); its loads, MMAs and first
+                                     softmax overlap that kernel's tail. Never set it when the producer of q/k may be the
+                                     immediately preceding kernel on `stream`. Ordering of the accumulator updates, and
+                                     therefore the result, is unchanged. */
 
 /*
  * One traced cross-attention layer call: the conditional half of the projections `to_q(hidden_states)` and

@@ -14,6 +14,10 @@ Fixtures
                      ``compute_global_heat_map`` for several filters / normalize (row a7), word maps (a8), expand_as (a10).
   pipeline_tiny.npz  a 2-step generation of the TINY synthetic pipeline under the reference's ``trace``: global heat
                      map, normalised map, filtered maps, per-key sums (rows a1-a9 end to end).
+  pipeline_tiny96.npz the same for the 96x96-latent geometry of the 768-pixel models (latent_hw 9216, trace.py:32-33):
+                     (96, 96) global maps from keys at 96^2 / 48^2 / 24^2.
+  perkey.npz         the reference's --all-heads sweep (daam/run/generate.py:239-255) over finalize.npz's keys:
+                     ``compute_global_heat_map(layer_idx=l, head_idx=h)`` for every key, plain and normalised.
 """
 from __future__ import annotations
 
@@ -27,7 +31,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from daam_b200.synthetic import TINY_SPEC, SyntheticAttention, WhitespaceTokenizer, make_pipeline  # noqa: E402
+from daam_b200.testing.synthetic import TINY96_SPEC, TINY_SPEC, SyntheticAttention, WhitespaceTokenizer, make_pipeline  # noqa: E402
 from oracle.ref_loader import load_reference  # noqa: E402
 
 OUT = os.path.join(ROOT, 'tests', 'golden')
@@ -121,6 +125,43 @@ def make_pipeline_fixture(daam):
     print('pipeline', len(keys), {k: tuple(v.shape) for k, v in out.items()})
 
 
+def make_pipeline96_fixture(daam):
+    pipe = make_pipeline(TINY96_SPEC, dtype=torch.float32, seed=5)
+    with daam.trace(pipe) as tc:
+        assert tc.latent_hw == 9216
+        pipe(PROMPT, num_inference_steps=2, generator=torch.Generator().manual_seed(13))
+        keys = [k for k, _ in tc.all_heat_maps]
+        sums = np.array([float(v.double().sum()) for _, v in tc.all_heat_maps])
+        out = {
+            'global': tc.compute_global_heat_map().heat_maps.numpy(),
+            'global_norm': tc.compute_global_heat_map(normalize=True).heat_maps.numpy(),
+            'factors_4': tc.compute_global_heat_map(factors=[4]).heat_maps.numpy(),
+            'word_ball': tc.compute_global_heat_map().compute_word_heat_map('ball').heatmap.numpy(),
+        }
+    np.savez_compressed(os.path.join(OUT, 'pipeline_tiny96.npz'), prompt=PROMPT, steps=2, unet_seed=5, gen_seed=13,
+                        keys=np.array(keys), key_sums=sums, **out)
+    print('pipeline96', len(keys), {k: tuple(v.shape) for k, v in out.items()})
+
+
+def make_perkey_fixture(daam):
+    """Every (layer, head) map of the all-heads sweep, from the keys stored in finalize.npz."""
+    fx = np.load(os.path.join(OUT, 'finalize.npz'), allow_pickle=False)
+    coll = daam.RawHeatMapCollection()
+    order = []
+    for name in fx.files:
+        if name.startswith('key_'):
+            f, l, h = (int(v) for v in name.split('_')[1:])
+            coll.update(f, l, h, torch.from_numpy(fx[name]))
+            order.append((f, l, h))
+    fake = SimpleNamespace(all_heat_maps=coll, last_prompt=str(fx['prompt']), latent_hw=4096,
+                           pipe=SimpleNamespace(tokenizer=WhitespaceTokenizer()))
+    cg = daam.trace.compute_global_heat_map
+    plain = np.stack([cg(fake, layer_idx=l, head_idx=h).heat_maps.numpy() for f, l, h in order])
+    norm = np.stack([cg(fake, layer_idx=l, head_idx=h, normalize=True).heat_maps.numpy() for f, l, h in order])
+    np.savez_compressed(os.path.join(OUT, 'perkey.npz'), keys=np.array(order), plain=plain, norm=norm)
+    print('perkey', plain.shape)
+
+
 def main():
     warnings.filterwarnings('ignore', category=FutureWarning)
     os.makedirs(OUT, exist_ok=True)
@@ -130,6 +171,8 @@ def main():
     make_layers(daam)
     make_finalize(daam)
     make_pipeline_fixture(daam)
+    make_pipeline96_fixture(daam)
+    make_perkey_fixture(daam)
 
 
 if __name__ == '__main__':

@@ -2,7 +2,7 @@
 
 The reference cannot be imported as-is in this container: ``diffusers``, ``matplotlib``, ``spacy`` (and friends) are
 not installed and there is no network. None of those packages contributes arithmetic to the hot path
-except ``diffusers.models.attention_processor.Attention``, whose 0.21.2 semantics ``daam_b200.synthetic.
+except ``diffusers.models.attention_processor.Attention``, whose 0.21.2 semantics ``daam_b200.testing.synthetic.
 SyntheticAttention`` restates. This loader registers empty stand-in modules for the missing imports, points
 ``diffusers...Attention`` at that restatement, and then imports ``daam`` from the read-only reference tree.
 
@@ -34,7 +34,7 @@ def _stub(name: str, **attrs) -> types.ModuleType:
 
 
 def _install_stubs():
-    from daam_b200.synthetic import SyntheticAttention
+    from daam_b200.testing.synthetic import SyntheticAttention
 
     class _Empty:  # the reference only uses these names for annotations and one exact ``type(...) ==`` test
         pass

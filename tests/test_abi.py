@@ -35,7 +35,7 @@ def test_header_and_binding_agree():
 def test_every_declared_symbol_is_exported(lib):
     for name in declared_functions():
         assert hasattr(lib, name), f'{name} declared in include/daam_b200.h but not exported'
-    assert _native.abi_version() == 2
+    assert _native.abi_version() == _native.ABI_VERSION == 3
 
 
 def test_struct_layout_matches_the_header():

@@ -267,7 +267,7 @@ def test_full_size_sd21_step_properties():
 def test_materialised_probs_match_get_attention_scores(hw, heads, d, dtype, tol):
     """daam_attention_probs == diffusers' get_attention_scores (reference call at trace.py:276) for every sample;
     daam_accumulate_probs == _unravel_attn + update on that tensor. Tolerance: one rounding to the output dtype."""
-    from daam_b200.synthetic import SyntheticAttention
+    from daam_b200.testing.synthetic import SyntheticAttention
     g = torch.Generator().manual_seed(hw + d)
     q = torch.randn(2, hw, heads * d, generator=g).to(dtype).to(DEV)
     k = torch.randn(2, 77, heads * d, generator=g).to(dtype).to(DEV)

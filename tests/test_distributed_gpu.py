@@ -20,7 +20,7 @@ def _trace_prompt(pipe, prompt, seed):
 
 def _worker(rank, world, port, out_dir):
     from daam_b200.distributed import gather_heat_maps, shard_prompts
-    from daam_b200.synthetic import TINY_SPEC, make_pipeline
+    from daam_b200.testing.synthetic import TINY_SPEC, make_pipeline
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
@@ -36,7 +36,7 @@ def _worker(rank, world, port, out_dir):
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
 def test_sharded_prompts_and_nccl_gather(tmp_path):
     from daam_b200.distributed import pad_heat_map
-    from daam_b200.synthetic import TINY_SPEC, make_pipeline
+    from daam_b200.testing.synthetic import TINY_SPEC, make_pipeline
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
         port = s.getsockname()[1]

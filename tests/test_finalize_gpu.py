@@ -10,7 +10,7 @@ import torch
 
 from daam_b200 import _native
 from daam_b200.heatmap import GlobalHeatMap
-from daam_b200.synthetic import WhitespaceTokenizer
+from daam_b200.testing.synthetic import WhitespaceTokenizer
 from oracle import daam_oracle as O
 from tests.util import golden, rel_err
 

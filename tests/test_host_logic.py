@@ -7,7 +7,7 @@ from daam_b200 import trace
 from daam_b200.build import build
 from daam_b200.hook import AggregateHooker, ObjectHooker, UNetCrossAttentionLocator
 from daam_b200.ops import cond_half
-from daam_b200.synthetic import (SD21_SPEC, SDXL_SPEC, TINY_SPEC, SDPAProcessor, SyntheticUNet, WhitespaceTokenizer,
+from daam_b200.testing.synthetic import (SD21_SPEC, SDXL_SPEC, TINY_SPEC, SDPAProcessor, SyntheticUNet, WhitespaceTokenizer,
                                  make_pipeline)
 from daam_b200.utils import compute_token_merge_indices
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from daam_b200.synthetic import TINY_SPEC, WhitespaceTokenizer, make_pipeline
+from daam_b200.testing.synthetic import TINY96_SPEC, TINY_SPEC, WhitespaceTokenizer, make_pipeline
 from oracle import daam_oracle as O
 from tests.util import LAYER_FIXTURES, golden
 
@@ -99,3 +99,40 @@ def test_pipeline_fixture():
     hw = {1: 4096, 2: 1024, 4: 256}
     for (f, _, _), s in zip(fx['keys'].tolist(), fx['key_sums']):
         assert abs(s - 2 * hw[f]) < 1e-2 * hw[f]
+
+
+def test_pipeline96_fixture():
+    """96x96-latent geometry (768-pixel models, daam/trace.py:32-33): keys at 96^2 / 48^2 / 24^2, x = 96."""
+    fx = golden('pipeline_tiny96')
+    pipe = make_pipeline(TINY96_SPEC, dtype=torch.float32, seed=int(fx['unet_seed']))
+    with O.OracleTrace(pipe) as ot:
+        assert ot.latent_hw == 9216
+        pipe(str(fx['prompt']), num_inference_steps=int(fx['steps']),
+             generator=torch.Generator().manual_seed(int(fx['gen_seed'])))
+        assert [list(k) for k, _ in ot.heat_maps] == fx['keys'].tolist()
+        sums = np.array([float(v.double().sum()) for _, v in ot.heat_maps])
+        np.testing.assert_allclose(sums, fx['key_sums'], rtol=1e-6)
+        loose = dict(rtol=1e-4, atol=1e-6)
+        g = ot.compute_global_heat_map()
+        assert tuple(g.shape) == (11, 96, 96)
+        np.testing.assert_allclose(g.numpy(), fx['global'], **loose)
+        np.testing.assert_allclose(ot.compute_global_heat_map(normalize=True).numpy(), fx['global_norm'], **loose)
+        np.testing.assert_allclose(ot.compute_global_heat_map(factors=[4]).numpy(), fx['factors_4'], **loose)
+        np.testing.assert_allclose(O.port_word_heat_map(g, pipe.tokenizer, str(fx['prompt']), 'ball').numpy(),
+                                   fx['word_ball'], **loose)
+    hw = {1: 9216, 2: 2304, 4: 576}
+    for (f, _, _), s in zip(fx['keys'].tolist(), fx['key_sums']):
+        assert abs(s - 2 * hw[f]) < 1e-2 * hw[f]
+
+
+def test_per_key_sweep_port():
+    """The reference's --all-heads sweep (daam/run/generate.py:239-255): one compute_global_heat_map per (layer, head)."""
+    fx, pk = golden('finalize'), golden('perkey')
+    keys = _finalize_keys(fx)
+    n_tok = len(WhitespaceTokenizer().tokenize(str(fx['prompt'])))
+    assert [list(k) for k, _ in keys] == pk['keys'].tolist()
+    for i, (f, l, h) in enumerate(pk['keys'].tolist()):
+        np.testing.assert_allclose(O.port_global_heat_map(keys, 4096, n_tok, layer_idx=l, head_idx=h).numpy(),
+                                   pk['plain'][i], **TOL)
+        np.testing.assert_allclose(O.port_global_heat_map(keys, 4096, n_tok, layer_idx=l, head_idx=h,
+                                                          normalize=True).numpy(), pk['norm'][i], **TOL)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from daam_b200.synthetic import TINY_SPEC, make_pipeline
+from daam_b200.testing.synthetic import TINY_SPEC, make_pipeline
 from oracle import daam_oracle as O
 from oracle.ref_loader import load_reference, reference_available
 
@@ -160,3 +160,36 @@ def test_reference_experiment_dump_loads_in_daam_b200(ref, tmp_path):
     # cannot read ANY pickled experiment under torch >= 2.6, its own included, so the reverse direction is checked by name)
     listing = lambda root: sorted(str(p.relative_to(root)) for p in root.rglob('*') if p.is_file())
     assert listing(tmp_path / 'again') == listing(tmp_path / 'q1')
+
+
+def test_latent96_geometry_bit_equal(ref):
+    """768-pixel models (latent_hw 9216, daam/trace.py:32-33): reference and oracle bit-equal on the 96-latent tree,
+    including the full-size 96 x 96 = 9216-position layer."""
+    from daam_b200.testing.synthetic import TINY96_SPEC
+    pipe = make_pipeline(TINY96_SPEC, dtype=torch.float32, seed=5)
+    gen = lambda: torch.Generator().manual_seed(13)
+    with ref.trace(pipe) as tc:
+        assert tc.latent_hw == 9216
+        pipe(PROMPT, num_inference_steps=2, generator=gen())
+        ref_keys = {k: v.clone() for k, v in tc.all_heat_maps}
+        ref_g = tc.compute_global_heat_map(normalize=True).heat_maps.clone()
+    with O.OracleTrace(pipe) as ot:
+        pipe(PROMPT, num_inference_steps=2, generator=gen())
+        ora_keys = {k: v.clone() for k, v in ot.heat_maps}
+        ora_g = ot.compute_global_heat_map(normalize=True)
+    assert list(ref_keys) == list(ora_keys) and {v.shape[-1] for v in ref_keys.values()} == {96, 48, 24}
+    for k in ref_keys:
+        assert torch.equal(ref_keys[k], ora_keys[k]), k
+    assert ref_g.shape == (11, 96, 96) and torch.equal(ref_g, ora_g)
+
+
+def test_per_key_sweep_bit_equal(ref, runs):
+    """The --all-heads sweep (daam/run/generate.py:239-255): compute_global_heat_map(layer_idx, head_idx) per key."""
+    pipe, ref_keys, _, ora_keys, _ = runs
+    with ref.trace(pipe) as tc:
+        pipe(PROMPT, num_inference_steps=2, generator=torch.Generator().manual_seed(11))
+        for (f, l, h) in list(ref_keys)[::5]:
+            want = tc.compute_global_heat_map(layer_idx=l, head_idx=h, normalize=True).heat_maps
+            got = O.port_global_heat_map(list(ora_keys.items()), 4096, want.shape[0] - 2, layer_idx=l, head_idx=h,
+                                         normalize=True)
+            assert torch.equal(want, got), (f, l, h)

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from daam_b200 import trace
-from daam_b200.synthetic import TINY_SPEC, make_pipeline
+from daam_b200.testing.synthetic import TINY_SPEC, make_pipeline
 from oracle import daam_oracle as O
 from tests.util import golden, rel_err
 
@@ -274,7 +274,7 @@ def test_collection_interface_update_and_to_experiment(tmp_path):
 def test_sd1x_style_pipeline(dtype, tol):
     """SD-1.x style UNet (head_dim = channels // heads: 40 / 80 / 80): the tracer picks the K-chunked tcgen05 path; parity
     with the oracle on the identical Q/K the hooks saw."""
-    from daam_b200.synthetic import TINY15_SPEC
+    from daam_b200.testing.synthetic import TINY15_SPEC
     pipe = make_pipeline(TINY15_SPEC, dtype=dtype, device=DEV, seed=3)
     with trace(pipe) as tc:
         rec = Recorder(tc)
