@@ -17,12 +17,14 @@ DAAM_F32, DAAM_F16, DAAM_BF16 = 0, 1, 2
 ACC_AUTO, ACC_FORCE_SIMT, ACC_FORCE_MMA = 0, 1, 2
 ACC_RMW_AUTO, ACC_RMW_LDST, ACC_RMW_RED = 0x00, 0x10, 0x20
 ACC_NO_PDL = 0x100
+ACC_RED_SEGMENTS, ACC_RED_ROWS = 0x400, 0x800
 ACC_EARLY_LOADS = 0x200   # see include/daam_b200.h: only valid when q/k were complete before the previous kernel started
 ABI_VERSION = 3
 E_INVALID, E_UNSUPPORTED, E_CUDA = -1, -2, -3
 TOKENS = 77
+EXPAND_SCRATCH_FLOATS = 64   # DAAM_EXPAND_SCRATCH_FLOATS: per word
 
-EXPORTS = ('daam_accumulate', 'daam_attention_probs', 'daam_accumulate_probs', 'daam_finalize', 'daam_finalize_per_key', 'daam_word_heat_map', 'daam_expand_as', 'daam_abi_version',
+EXPORTS = ('daam_accumulate', 'daam_attention_probs', 'daam_accumulate_probs', 'daam_finalize', 'daam_finalize_per_key', 'daam_word_heat_map', 'daam_expand_as', 'daam_expand_words', 'daam_abi_version',
            'daam_last_error', 'daam_device_info', 'daam_launch_count')
 
 
@@ -85,8 +87,9 @@ def load() -> ctypes.CDLL:
     lib.daam_word_heat_map.restype = ctypes.c_int
     lib.daam_expand_as.argtypes = [vp, i32, i32, i32, i32, i32, f32, vp, vp, vp]
     lib.daam_expand_as.restype = ctypes.c_int
-    lib.daam_abi_version.argtypes = []
-    lib.daam_abi_version.restype = ctypes.c_int
+    lib.daam_expand_words.argtypes = [vp, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), i32, i32, i32, i32, i32, f32,
+                                      vp, vp, vp, vp]
+    lib.daam_expand_words.restype = ctypes.c_int
     lib.daam_last_error.argtypes = []
     lib.daam_last_error.restype = ctypes.c_char_p
     lib.daam_device_info.argtypes = [ctypes.POINTER(i32)] * 3
@@ -155,6 +158,23 @@ def expand_as(map_ptr: int, x: int, out_h: int, out_w: int, absolute: bool, thre
     _check(load().daam_expand_as(ctypes.c_void_p(map_ptr), x, out_h, out_w, int(bool(absolute)), int(use_thr),
                                  float(threshold) if use_thr else 0.0, ctypes.c_void_p(out_ptr),
                                  ctypes.c_void_p(scratch_ptr), ctypes.c_void_p(stream)))
+
+
+def expand_words(maps_ptr: int, n_rows: int, x: int, rows_per_word: Sequence[Sequence[int]], out_h: int, out_w: int,
+                 absolute: bool, threshold: Optional[float], word_maps_ptr: Optional[int], out_ptr: int, scratch_ptr: int,
+                 stream: int):
+    """``rows_per_word[w]``: the rows of ``maps`` word ``w`` averages (already offset for SOS)."""
+    flat = [r for rows in rows_per_word for r in rows]
+    begin = [0]
+    for rows in rows_per_word:
+        begin.append(begin[-1] + len(rows))
+    rows_arr = (ctypes.c_int32 * max(len(flat), 1))(*flat)
+    begin_arr = (ctypes.c_int32 * len(begin))(*begin)
+    use_thr = bool(threshold)   # the reference's `if threshold:` (daam/heatmap.py:87)
+    _check(load().daam_expand_words(ctypes.c_void_p(maps_ptr), n_rows, x, rows_arr, begin_arr, len(rows_per_word), out_h,
+                                    out_w, int(bool(absolute)), int(use_thr), float(threshold) if use_thr else 0.0,
+                                    ctypes.c_void_p(word_maps_ptr) if word_maps_ptr else None,
+                                    ctypes.c_void_p(out_ptr), ctypes.c_void_p(scratch_ptr), ctypes.c_void_p(stream)))
 
 
 def device_info():

@@ -63,7 +63,10 @@ struct MmaParams {
   CUtensorMap qmap[kMaxLayersPerLaunch];
   CUtensorMap kmap[kMaxLayersPerLaunch];
   CUtensorMap amap[kMaxLayersPerLaunch];
+  CUtensorMap amap_seg[kMaxLayersPerLaunch];       // same tensor, box = [11 tokens x 128 pixels] (segmented reduce)
 };
+constexpr int kSegTokens = 11, kSegs = kTokens / kSegTokens;        // 77 = 7 x 11
+static_assert(kSegs * kSegTokens == kTokens, "token segments must tile 77");
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -112,6 +115,12 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
                "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void bulk_reduce_add_1d(float* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -432,6 +441,40 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
           bulk_commit();
         }
         issued = true;
+      } else if (P.rmw_mode == 2) {
+        // segmented: 7 reduce-adds of 11 token rows each, one bulk group per segment, so that segment g of this tile
+        // only waits for segment g of the previous tile (up to 7 reduces in flight per CTA instead of 1)
+#pragma unroll
+        for (int g = 0; g < kSegs; ++g) {
+          if (tid == 0 && issued) bulk_wait_read<kSegs - 1>();
+          epi_barrier();
+#pragma unroll
+          for (int j = g * kSegTokens; j < (g + 1) * kSegTokens; ++j) sP[j * kTilePixels + tid] = v[j] * inv;
+          fence_proxy_async();
+          epi_barrier();
+          if (tid == 0) {
+            tma_reduce_add_2d(&MP.amap_seg[t.li], sP_u32 + g * kSegTokens * kTilePixels * 4, t.pixel0,
+                              (t.prompt * L.heads + t.head) * kTokens + g * kSegTokens);
+            bulk_commit();
+          }
+        }
+        issued = true;
+      } else if (P.rmw_mode == 3) {
+        // row reduces: thread j < 77 owns token row j of the staged tile and sends it as its own 1-D bulk reduce-add
+        // (77 independent bulk groups in flight per CTA; bytes clip partial tiles)
+        if (tid < kTokens && issued) bulk_wait_read0();
+        epi_barrier();
+#pragma unroll
+        for (int j = 0; j < kTokens; ++j) sP[j * kTilePixels + tid] = v[j] * inv;
+        fence_proxy_async();
+        epi_barrier();
+        if (tid < kTokens) {
+          const int live = min(kTilePixels, L.hw - t.pixel0);
+          float* dst = L.acc + ((long long)(t.prompt * L.heads + t.head) * kTokens + tid) * L.hw + t.pixel0;
+          bulk_reduce_add_1d(dst, sP_u32 + tid * kTilePixels * 4, (uint32_t)live * 4u);
+          bulk_commit();
+        }
+        issued = true;
       } else {
         const int pixel = t.pixel0 + tid;
         if (pixel < L.hw) {
@@ -450,7 +493,7 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
       }
     }
     // shared memory must outlive the reduce's reads; its global writes complete with the grid (same rule as a TMA store)
-    if (tid == 0 && issued) bulk_wait_read0();
+    if (issued && (tid == 0 || (P.rmw_mode == 3 && tid < kTokens))) bulk_wait_read0();
   }
 
   tc_fence_before();
@@ -535,9 +578,9 @@ int make_qk_map(const void* ptr, int dtype, int head_dim, int heads, int rows, i
   return DAAM_OK;
 }
 
-// accumulator as a 2-D fp32 tensor {hw, prompts*heads*77}; box = [77 tokens x 128 pixels], no swizzle.
-int make_acc_map(float* acc, int hw, int rows, CUtensorMap* out) {
-  MapKey key{acc, 0, 0, 0, hw, rows, 0, 1};
+// accumulator as a 2-D fp32 tensor {hw, prompts*heads*77}; box = [box_tokens x 128 pixels], no swizzle.
+int make_acc_map(float* acc, int hw, int rows, int box_tokens, CUtensorMap* out) {
+  MapKey key{acc, 0, 0, 0, hw, rows, box_tokens, 1};
   {
     std::lock_guard<std::mutex> lock(g_map_mu);
     auto it = map_cache().find(key);
@@ -547,7 +590,7 @@ int make_acc_map(float* acc, int hw, int rows, CUtensorMap* out) {
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DAAM_E_CUDA; }
   const cuuint64_t dims[2] = {(cuuint64_t)hw, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)hw * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)kTilePixels, (cuuint32_t)kTokens};
+  const cuuint32_t box[2] = {(cuuint32_t)kTilePixels, (cuuint32_t)box_tokens};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, acc, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -589,7 +632,8 @@ int prepare_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, void* o
     if ((L.dtype == DAAM_F32) != split) { set_error("mixed fp32 / 16-bit layers in one tcgen05 pack"); return DAAM_E_INVALID; }
     if (int rc = make_qk_map(L.q, L.dtype, L.head_dim, L.heads, L.hw, L.n_prompts, L.qs_head, L.qs_pixel, L.qs_prompt, kTilePixels, &mp.qmap[i])) return rc;
     if (int rc = make_qk_map(L.k, L.dtype, L.head_dim, L.heads, kTokens, L.n_prompts, L.ks_head, L.ks_token, L.ks_prompt, kTokensPad, &mp.kmap[i])) return rc;
-    if (int rc = make_acc_map(L.acc, L.hw, L.n_prompts * L.heads * kTokens, &mp.amap[i])) return rc;
+    if (int rc = make_acc_map(L.acc, L.hw, L.n_prompts * L.heads * kTokens, kTokens, &mp.amap[i])) return rc;
+    if (int rc = make_acc_map(L.acc, L.hw, L.n_prompts * L.heads * kTokens, kSegTokens, &mp.amap_seg[i])) return rc;
     chunked = chunked || L.head_dim > 64;
   }
   cudaError_t attr_err = cudaSuccess;

@@ -6,8 +6,11 @@
 // The interpolation is torch's `upsample_bicubic2d` with align_corners=False: source index
 // (dst + 0.5) * in/out - 0.5 (not clamped), Keys' cubic convolution with A = -0.75 on the 4 taps floor-1..floor+2,
 // taps clamped to the border; rows are combined horizontally first, then vertically, all in fp32.
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
+
+#include <mutex>
 
 #include "common.cuh"
 
@@ -96,15 +99,19 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ F
 
 
 // ---- fast path: integer upsampling factors 1 / 2 / 4 -------------------------------------------------------------
-// One CTA owns one output band (16 rows x x columns) of one token row and walks the key classes (distinct source
-// resolutions) one after the other. Within a class a thread owns ONE source pixel and produces its F x F output block:
-// with an integer factor the cubic weights depend only on the output phase (F distinct weight sets per axis), and the
-// F x F outputs of a source pixel read the same 5 x 5 source window -- 25 loads and 9-14 FMAs per output instead of 16
-// loads and 20 FMAs per output for the generic gather. When a class has fewer source pixels per band than threads, the
-// spare thread groups take every kg-th key and the groups are merged through the shared-memory band in a fixed order
-// (deterministic sums). Arithmetic per key is bit-identical to bicubic_at (same taps, same weights, same order).
-constexpr int kBandRows = 8;
+// One CTA owns one output band (BR = 8 or 4 rows x x columns) of one token row and walks the key classes (distinct
+// source resolutions) one after the other. With an integer factor F the cubic weights depend only on the output phase
+// (F distinct weight sets per axis), and the F x F outputs under one source pixel read the same 5 x 5 source window: a
+// thread owns ONE source pixel and emits its F x F outputs from one window (25 values, 9-14 FMAs per output).
+// The windows come from shared memory: the band's source rows (+2 halo rows each side, clamped at the borders) of a
+// CHUNK of keys are streamed in with 16-byte cp.async (every thread has several independent copies in flight, two
+// chunks double-buffered), so the key loop is no longer a chain of dependent global loads -- the round-1 kernel's bound
+// (34.8 us for the 175-key SD-2.1 case, 222 registers, 0.86 waves) -- and the kernel fits two CTAs per SM.
+// When a class has fewer source pixels per band than threads, the spare thread groups take every kg-th key and the
+// groups are merged through the shared-memory band in a fixed order (deterministic sums). Arithmetic per key is
+// bit-identical to bicubic_at (same taps, same weights, same order).
 constexpr int kMaxClassKeys = 2048;        // key pointers of one class staged in shared memory
+constexpr int kStageFloats = 4096;         // one chunk buffer (16 KB); two of them
 
 template <int F>
 struct PhaseWeights {
@@ -126,6 +133,7 @@ struct PhaseWeights {
 // Fills keys[] (shared) with the source pointer (token row t) of every selected key of the class; returns the count.
 __device__ __forceinline__ int stage_class_keys(const FinalizeParams& P, int cls_side, int t, const float** keys) {
   __shared__ int n_keys_s;
+  __syncthreads();                                     // the previous class is done with keys[]
   if (threadIdx.x == 0) {
     int n = 0;
     for (int g = 0; g < P.n_groups; ++g) {
@@ -140,14 +148,6 @@ __device__ __forceinline__ int stage_class_keys(const FinalizeParams& P, int cls
   }
   __syncthreads();
   return n_keys_s;
-}
-
-template <int F>
-__device__ __forceinline__ void load_window(const float* src, const int (&iy)[5], const int (&ix)[5], float (&v)[5][5]) {
-#pragma unroll
-  for (int i = 0; i < 5; ++i)
-#pragma unroll
-    for (int j = 0; j < 5; ++j) v[i][j] = __ldg(src + iy[i] + ix[j]);
 }
 
 template <int F>
@@ -176,65 +176,94 @@ __device__ __forceinline__ void add_key(const PhaseWeights<F>& pw, const float (
   }
 }
 
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int F>
-__device__ __forceinline__ void class_pass(const FinalizeParams& P, int cls_h, int t, int band, float* tile,
-                                           const float** keys) {
-  constexpr int R = kBandRows / F;                     // source rows under this band
-  const int x = P.x, w = cls_h, h = cls_h;
-  const int n_src = R * w;
-  const int kg = n_src >= 256 ? 1 : 256 / n_src;       // thread groups that split the keys
-  const int passes = (n_src + 255) / 256;
-  const int nk = stage_class_keys(P, cls_h, t, keys);
+__device__ __forceinline__ void class_pass(const FinalizeParams& P, int side, int t, int band, int br, float* tile,
+                                           const float** keys, float* stage) {
+  const int x = P.x;
+  const int R = br / F;                                // source rows under this band
+  const int VR = R + 4;                                // + 2 halo rows above and below
+  const int region = VR * side;                        // floats of one key's staged rows
+  const int n_src = R * side;                          // source pixels under the band (<= 256, checked by the host)
+  const int kg = 256 / n_src;                          // thread groups that split the keys
+  int kc = kStageFloats / region;                      // keys per chunk, a multiple of kg so every group keeps its stride
+  kc -= kc % kg;
+  const int nk = stage_class_keys(P, side, t, keys);
+  const int n_chunks = (nk + kc - 1) / kc;
+  const int row_units = side / 4, key_units = VR * row_units;     // 16-byte units
+  const int sy0 = band * R;
+
+  auto issue = [&](int c) {
+    float* buf = stage + (c & 1) * kStageFloats;
+    const int k0 = c * kc, kn = min(kc, nk - k0);
+    for (int u = threadIdx.x; u < kn * key_units; u += blockDim.x) {
+      const int k = u / key_units, rem = u - k * key_units;
+      const int vr = rem / row_units, c4 = rem - vr * row_units;
+      const int row = min(max(sy0 - 2 + vr, 0), side - 1);          // border rows are replicated, as the taps clamp
+      cp_async16(buf + k * region + vr * side + 4 * c4, keys[k0 + k] + row * side + 4 * c4);
+    }
+    cp_async_commit();
+  };
+
+  const int group = (int)threadIdx.x / n_src;
+  const int s = (int)threadIdx.x - group * n_src;
+  const bool live = group < kg;
+  const int ly = s / side, sx = s - ly * side;
+  int ix[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) ix[j] = min(max(sx - 2 + j, 0), side - 1);
   PhaseWeights<F> pw;
   pw.init();
-  for (int pass = 0; pass < passes; ++pass) {
-    const int group = n_src >= 256 ? 0 : (int)threadIdx.x / n_src;
-    const int s = n_src >= 256 ? pass * 256 + (int)threadIdx.x : (int)threadIdx.x % n_src;
-    const bool live = s < n_src && group < kg;
-    const int sy = band * R + s / w, sx = s % w;
-    int iy[5], ix[5];
+  float acc[F][F];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      iy[i] = min(max(sy - 2 + i, 0), h - 1) * w;
-      ix[i] = min(max(sx - 2 + i, 0), w - 1);
-    }
-    float acc[F][F];
+  for (int py = 0; py < F; ++py)
 #pragma unroll
-    for (int py = 0; py < F; ++py)
-#pragma unroll
-      for (int px = 0; px < F; ++px) acc[py][px] = 0.f;
+    for (int px = 0; px < F; ++px) acc[py][px] = 0.f;
+
+  if (n_chunks > 0) issue(0);
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c + 1 < n_chunks) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();                                   // chunk c has landed for every thread
     if (live) {
-      // two windows in flight: the loads of the next key are issued before the arithmetic of the current one
-      float va[5][5], vb[5][5];
-      int k = group;
-      if (k < nk) load_window<F>(keys[k], iy, ix, va);
-      for (; k < nk; k += 2 * kg) {
-        const bool has_b = k + kg < nk;
-        if (has_b) load_window<F>(keys[k + kg], iy, ix, vb);
-        add_key<F>(pw, va, acc);
-        if (k + 2 * kg < nk) load_window<F>(keys[k + 2 * kg], iy, ix, va);
-        if (has_b) add_key<F>(pw, vb, acc);
+      const float* buf = stage + (c & 1) * kStageFloats + ly * side;
+      const int kn = min(kc, nk - c * kc);
+      for (int k = group; k < kn; k += kg) {
+        const float* src = buf + k * region;
+        float v[5][5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+          for (int j = 0; j < 5; ++j) v[i][j] = src[i * side + ix[j]];
+        add_key<F>(pw, v, acc);
       }
     }
-    for (int g = 0; g < kg; ++g) {                      // merge the key groups in a fixed order
-      if (live && group == g) {
-        const int oy0 = (s / w) * F, ox0 = sx * F;
+    __syncthreads();                                   // buffer (c & 1) may be overwritten by chunk c + 2
+  }
+  for (int g = 0; g < kg; ++g) {                       // merge the key groups in a fixed order
+    if (live && group == g) {
+      const int oy0 = ly * F, ox0 = sx * F;
 #pragma unroll
-        for (int py = 0; py < F; ++py)
+      for (int py = 0; py < F; ++py)
 #pragma unroll
-          for (int px = 0; px < F; ++px) tile[(oy0 + py) * x + ox0 + px] += acc[py][px];
-      }
-      __syncthreads();
+        for (int px = 0; px < F; ++px) tile[(oy0 + py) * x + ox0 + px] += acc[py][px];
     }
+    __syncthreads();
   }
 }
 
 // factor 1: bicubic at scale 1 is the identity, the class contributes clamp(src) -- coalesced float4 reads; when the
 // band has fewer float4s than threads, the spare thread groups take every kg-th key (merged in a fixed order)
-__device__ __forceinline__ void class_pass_identity(const FinalizeParams& P, int t, int band, float* tile,
+__device__ __forceinline__ void class_pass_identity(const FinalizeParams& P, int t, int band, int br, float* tile,
                                                     const float** keys) {
   const int x = P.x;
-  const int n4 = kBandRows * x / 4;
+  const int n4 = br * x / 4;
   const int nk = stage_class_keys(P, x, t, keys);
   const int kg = n4 >= 256 ? 1 : 256 / n4;
   const int passes = (n4 + 255) / 256;
@@ -244,8 +273,8 @@ __device__ __forceinline__ void class_pass_identity(const FinalizeParams& P, int
     const bool live = i < n4 && group < kg;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) {
-      const long long off = (long long)band * kBandRows * x + 4 * i;
-#pragma unroll 4
+      const long long off = (long long)band * br * x + 4 * i;
+#pragma unroll 8
       for (int k = group; k < nk; k += kg) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(keys[k] + off));
         acc.x += fmaxf(v.x, 0.f); acc.y += fmaxf(v.y, 0.f); acc.z += fmaxf(v.z, 0.f); acc.w += fmaxf(v.w, 0.f);
@@ -265,26 +294,29 @@ __device__ __forceinline__ void class_pass_identity(const FinalizeParams& P, int
 
 struct ClassList {
   int n;
+  int band_rows;    // 8, or 4 when that is what fills the machine / keeps a band's source pixels within one CTA
   int side[8];      // distinct source sides, all dividing x with factor 1, 2 or 4
 };
 
-// grid: (x / kBandRows bands, n_rows); dynamic smem: kBandRows * x floats
-__global__ void __launch_bounds__(256) finalize_fast_kernel(const __grid_constant__ FinalizeParams P,
-                                                            const __grid_constant__ ClassList C,
-                                                            float* __restrict__ out) {
-  extern __shared__ __align__(16) float tile[];
+// grid: (x / band_rows bands, n_rows); dynamic smem: band tile (band_rows * x floats) + two chunk buffers
+__global__ void __launch_bounds__(256, 2) finalize_fast_kernel(const __grid_constant__ FinalizeParams P,
+                                                               const __grid_constant__ ClassList C,
+                                                               float* __restrict__ out) {
+  extern __shared__ __align__(16) float dyn[];
   __shared__ const float* keys[kMaxClassKeys];
-  const int band = blockIdx.x, t = blockIdx.y, x = P.x;
-  for (int i = threadIdx.x; i < kBandRows * x; i += blockDim.x) tile[i] = 0.f;
-  __syncthreads();
+  float* stage = dyn;                                  // 2 x kStageFloats
+  float* tile = dyn + 2 * kStageFloats;
+  const int band = blockIdx.x, t = blockIdx.y, x = P.x, br = C.band_rows;
+  for (int i = threadIdx.x; i < br * x; i += blockDim.x) tile[i] = 0.f;
   for (int c = 0; c < C.n; ++c) {
     const int side = C.side[c], f = x / side;
-    if (f == 1) class_pass_identity(P, t, band, tile, keys);
-    else if (f == 2) class_pass<2>(P, side, t, band, tile, keys);
-    else class_pass<4>(P, side, t, band, tile, keys);
+    if (f == 1) class_pass_identity(P, t, band, br, tile, keys);
+    else if (f == 2) class_pass<2>(P, side, t, band, br, tile, keys, stage);
+    else class_pass<4>(P, side, t, band, br, tile, keys, stage);
   }
-  float* dst = out + (long long)t * x * x + (long long)band * kBandRows * x;
-  for (int i = threadIdx.x; i < kBandRows * x; i += blockDim.x) dst[i] = tile[i] / (float)P.n_keys;
+  __syncthreads();
+  float* dst = out + (long long)t * x * x + (long long)band * br * x;
+  for (int i = threadIdx.x; i < br * x; i += blockDim.x) dst[i] = tile[i] / (float)P.n_keys;
 }
 
 // One output map per selected key (no mean): out[key][row][x][x] = clamp(bicubic(key[row])). grid: (ceil(x*x/256), n_rows,
@@ -341,51 +373,96 @@ __global__ void word_map_kernel(const float* __restrict__ maps, const __grid_con
   out[o] = s / (float)sel.n;
 }
 
-// ---- expand_as ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned ordered(float f) {   // monotone float -> uint map for atomicMin/Max
-  const unsigned u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float unordered(unsigned u) {
-  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
+// ---- fused word list -> image-size masks -------------------------------------------------------------------------
+// One cooperative launch for a LIST of words: gather-mean of the word's rows of the global map (heatmap.py:121-123) ->
+// bicubic to (out_h, out_w) -> min / max over the image -> normalise / threshold (heatmap.py:77-93). CTA = (word, chunk
+// of output pixels). The word map lives in shared memory; the min/max pass and the write pass both interpolate from it
+// (16 shared loads + 20 FMAs per pixel), so nothing but the final image is written and nothing is read back: per-chunk
+// partial min/max go through `scratch`, one grid-wide barrier separates the passes. With `absolute` there is no
+// min/max pass and no barrier. Deterministic (no atomics).
+constexpr int kMaxWords = 96;
+constexpr int kMaxWordRows = 320;       // selected rows over all words of a launch
+constexpr int kMaxChunks = 32;          // CTAs per word; scratch holds 2 floats per (word, chunk)
 
-__global__ void expand_init_kernel(unsigned* mm) { mm[0] = 0xffffffffu; mm[1] = 0u; }
+struct ExpandWordsParams {
+  const float* maps;                    // [n_map_rows][x][x]
+  float* word_maps;                     // optional [n_words][x][x]
+  float* out;                           // [n_words][oh][ow]
+  float* scratch;                       // [n_words][chunks][2]
+  int x, oh, ow, n_words, chunks, absolute, use_threshold;
+  float threshold;
+  int row_begin[kMaxWords + 1];
+  int rows[kMaxWordRows];
+};
 
-__global__ void __launch_bounds__(256) expand_upsample_kernel(const float* __restrict__ src, int x, int oh, int ow,
-                                                              float* __restrict__ out, unsigned* mm) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ float bicubic_shared(const float* sm, int w, const Taps& ty, const Taps& tx) {
   float v = 0.f;
-  const bool live = o < oh * ow;
-  if (live) {
-    const int oy = o / ow, ox = o - oy * ow;
-    const Taps ty = make_taps(oy, x, oh), tx = make_taps(ox, x, ow);
-    v = bicubic_at(src, x, ty, tx);
-    out[o] = v;
-  }
-  float lo = live ? v : INFINITY, hi = live ? v : -INFINITY;
 #pragma unroll
-  for (int s = 16; s > 0; s >>= 1) {
-    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, s));
-    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+  for (int i = 0; i < 4; ++i) {
+    const float* row = sm + ty.idx[i] * w;
+    float r = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r += tx.w[j] * row[tx.idx[j]];
+    v += ty.w[i] * r;
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomicMin(mm, ordered(lo));
-    atomicMax(mm + 1, ordered(hi));
-  }
+  return v;
 }
 
-__global__ void expand_normalize_kernel(float* __restrict__ out, int n, const unsigned* __restrict__ mm, int absolute,
-                                        int use_threshold, float threshold) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= n) return;
-  float v = out[o];
-  if (!absolute) {
-    const float lo = unordered(mm[0]), hi = unordered(mm[1]);
-    v = (v - lo) / (hi - lo + 1e-8f);
+__global__ void __launch_bounds__(256) expand_words_kernel(const __grid_constant__ ExpandWordsParams P) {
+  extern __shared__ __align__(16) float wm[];          // the word map [x][x]
+  __shared__ float red_lo[8], red_hi[8];
+  const int word = blockIdx.x / P.chunks, chunk = blockIdx.x - word * P.chunks;
+  const int x = P.x, xx = x * x, n = P.oh * P.ow;
+  const int r0 = P.row_begin[word], r1 = P.row_begin[word + 1];
+  for (int i = threadIdx.x; i < xx; i += blockDim.x) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += __ldg(P.maps + (long long)P.rows[r] * xx + i);
+    s = s / (float)(r1 - r0);
+    wm[i] = s;
+    if (chunk == 0 && P.word_maps) P.word_maps[(long long)word * xx + i] = s;
   }
-  if (use_threshold) v = v > threshold ? 1.f : 0.f;
-  out[o] = v;
+  __syncthreads();
+  const int per = (n + P.chunks - 1) / P.chunks;
+  const int begin = chunk * per, end = min(n, begin + per);
+  float lo = 0.f, hi = 0.f;
+  if (!P.absolute) {
+    lo = INFINITY; hi = -INFINITY;
+    for (int o = begin + threadIdx.x; o < end; o += blockDim.x) {
+      const int oy = o / P.ow, ox = o - oy * P.ow;
+      const float v = bicubic_shared(wm, x, make_taps(oy, x, P.oh), make_taps(ox, x, P.ow));
+      lo = fminf(lo, v); hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, s));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, s));
+    }
+    if ((threadIdx.x & 31) == 0) { red_lo[threadIdx.x >> 5] = lo; red_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < (int)blockDim.x / 32; ++i) { lo = fminf(lo, red_lo[i]); hi = fmaxf(hi, red_hi[i]); }
+      float* slot = P.scratch + 2 * ((long long)word * P.chunks + chunk);
+      slot[0] = lo; slot[1] = hi;
+      __threadfence();
+    }
+    cooperative_groups::this_grid().sync();
+    if (threadIdx.x == 0) {
+      lo = INFINITY; hi = -INFINITY;
+      const volatile float* slots = P.scratch + 2 * (long long)word * P.chunks;
+      for (int c = 0; c < P.chunks; ++c) { lo = fminf(lo, slots[2 * c]); hi = fmaxf(hi, slots[2 * c + 1]); }
+      red_lo[0] = lo; red_hi[0] = hi;
+    }
+    __syncthreads();
+    lo = red_lo[0]; hi = red_hi[0];
+  }
+  float* dst = P.out + (long long)word * n;
+  for (int o = begin + threadIdx.x; o < end; o += blockDim.x) {
+    const int oy = o / P.ow, ox = o - oy * P.ow;
+    float v = bicubic_shared(wm, x, make_taps(oy, x, P.oh), make_taps(ox, x, P.ow));
+    if (!P.absolute) v = (v - lo) / (hi - lo + 1e-8f);
+    if (P.use_threshold) v = v > P.threshold ? 1.f : 0.f;
+    dst[o] = v;
+  }
 }
 
 }  // namespace
@@ -420,14 +497,15 @@ extern "C" int daam_finalize(const daam_key_group* groups, int32_t n_groups, int
     p.n_keys += g.head_sel < 0 ? g.heads : 1;
   }
   const int xx = x * x;
-  // fast path: every key is square with an integer factor 1 / 2 / 4 (all SD / SDXL layers that are ever traced)
+  // fast path: every key is square with an integer factor 1 / 2 / 4 (all SD / SDXL layers that are ever traced) and
+  // 16-byte-aligned rows (cp.async / float4)
   ClassList cls;
   cls.n = 0;
-  bool fast = x % kBandRows == 0 && x % 4 == 0 && x <= 256 && p.n_keys <= kMaxClassKeys && !force_generic_finalize();
+  bool fast = x % 16 == 0 && x <= 256 && p.n_keys <= kMaxClassKeys && !force_generic_finalize();
   for (int i = 0; i < n_groups && fast; ++i) {
     const daam_key_group& g = groups[i];
     if (g.h != g.w || x % g.h != 0 || (x / g.h != 1 && x / g.h != 2 && x / g.h != 4) ||
-        (x / g.h == 1 && reinterpret_cast<uintptr_t>(g.acc) % 16 != 0)) { fast = false; break; }
+        reinterpret_cast<uintptr_t>(g.acc) % 16 != 0) { fast = false; break; }
     bool seen = false;
     for (int c = 0; c < cls.n; ++c) seen = seen || cls.side[c] == g.h;
     if (!seen) {
@@ -436,7 +514,18 @@ extern "C" int daam_finalize(const daam_key_group* groups, int32_t n_groups, int
     }
   }
   if (fast) {
-    finalize_fast_kernel<<<dim3(x / kBandRows, n_rows), 256, kBandRows * x * sizeof(float), stream>>>(p, cls, out);
+    // 8-row bands unless that leaves the machine under-filled (< 2 CTAs per SM) or a band's source pixels of the
+    // factor-2 class would exceed one CTA's 256 threads (x > 128)
+    cls.band_rows = ((x / 8) * n_rows >= 2 * dev.sm_count && x <= 128) ? 8 : 4;
+    const size_t smem = (2 * kStageFloats + (size_t)cls.band_rows * x) * sizeof(float);
+    static std::once_flag attr_once[64];
+    cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once[dev.device & 63], [&] {
+      attr_err = cudaFuncSetAttribute(finalize_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((2 * kStageFloats + 8 * 256) * sizeof(float)));
+    });
+    DAAM_CUDA_TRY(attr_err);
+    finalize_fast_kernel<<<dim3(x / cls.band_rows, n_rows), 256, smem, stream>>>(p, cls, out);
   } else {
     dim3 grid((xx + 255) / 256, n_rows);
     finalize_kernel<<<grid, 256, 0, stream>>>(p, out);
@@ -508,18 +597,89 @@ extern "C" int daam_word_heat_map(const float* global_maps, int32_t n_rows, int3
   return DAAM_OK;
 }
 
-extern "C" int daam_expand_as(const float* word_map, int32_t x, int32_t out_h, int32_t out_w, int32_t absolute,
-                              int32_t use_threshold, float threshold, float* out, float* scratch, void* stream_) {
+static int launch_expand_words(ExpandWordsParams& p, const DeviceInfo& dev, cudaStream_t stream) {
+  const size_t smem = (size_t)p.x * p.x * sizeof(float);
+  static std::mutex mu;
+  static size_t configured_dev[64] = {};
+  static int blocks_per_sm[64] = {};
+  int per_sm;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& configured = configured_dev[dev.device & 63];
+    if (smem > configured) {
+      if (smem > 48 * 1024)
+        DAAM_CUDA_TRY(cudaFuncSetAttribute(expand_words_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+      blocks_per_sm[dev.device & 63] = 0;
+    }
+    if (blocks_per_sm[dev.device & 63] == 0) {
+      int occ = 0;
+      DAAM_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, expand_words_kernel, 256, configured));
+      blocks_per_sm[dev.device & 63] = occ < 1 ? 1 : occ;
+    }
+    per_sm = blocks_per_sm[dev.device & 63];
+  }
+  const int capacity = per_sm * dev.sm_count;          // a cooperative grid must be co-resident
+  const int n = p.oh * p.ow;
+  int done = 0;
+  const int total = p.n_words;
+  ExpandWordsParams q = p;
+  while (done < total) {                                // more words than the device holds at once: several launches
+    const int batch = total - done < capacity ? total - done : capacity;
+    int chunks = capacity / batch;
+    if (chunks > kMaxChunks) chunks = kMaxChunks;
+    if (chunks > (n + 255) / 256) chunks = (n + 255) / 256;
+    if (chunks < 1) chunks = 1;
+    q.n_words = batch;
+    q.chunks = chunks;
+    q.out = p.out + (long long)done * n;
+    q.word_maps = p.word_maps ? p.word_maps + (long long)done * p.x * p.x : nullptr;
+    q.scratch = p.scratch + 2LL * kMaxChunks * done;
+    for (int i = 0; i <= batch; ++i) q.row_begin[i] = p.row_begin[done + i];
+    void* args[] = {&q};
+    DAAM_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)expand_words_kernel, dim3(batch * chunks), dim3(256), args, smem,
+                                              stream));
+    count_launch();
+    done += batch;
+  }
+  return DAAM_OK;
+}
+
+extern "C" int daam_expand_words(const float* global_maps, int32_t n_rows, int32_t x, const int32_t* rows,
+                                 const int32_t* row_begin, int32_t n_words, int32_t out_h, int32_t out_w,
+                                 int32_t absolute, int32_t use_threshold, float threshold, float* word_maps, float* out,
+                                 float* scratch, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (!word_map || !out || !scratch || x <= 0 || out_h <= 0 || out_w <= 0) { set_error("daam_expand_as: null pointer or non-positive size"); return DAAM_E_INVALID; }
+  if (!global_maps || !rows || !row_begin || !out || !scratch || x <= 0 || out_h <= 0 || out_w <= 0 || n_rows <= 0) { set_error("daam_expand_words: null pointer or non-positive size"); return DAAM_E_INVALID; }
+  if (n_words <= 0) { set_error("daam_expand_words: empty word list"); return DAAM_E_INVALID; }
+  if (n_words > kMaxWords) { set_error("daam_expand_words: %d words > %d", n_words, kMaxWords); return DAAM_E_UNSUPPORTED; }
+  if (row_begin[0] != 0 || row_begin[n_words] > kMaxWordRows) { set_error("daam_expand_words: row_begin must start at 0 and select at most %d rows", kMaxWordRows); return DAAM_E_UNSUPPORTED; }
+  if ((size_t)x * x * sizeof(float) > 200 * 1024) { set_error("daam_expand_words: x = %d does not fit shared memory", x); return DAAM_E_UNSUPPORTED; }
   DeviceInfo dev;
   if (int rc = get_device_info(&dev)) return rc;
-  unsigned* mm = reinterpret_cast<unsigned*>(scratch);
-  const int n = out_h * out_w;
-  expand_init_kernel<<<1, 1, 0, stream>>>(mm);
-  expand_upsample_kernel<<<(n + 255) / 256, 256, 0, stream>>>(word_map, x, out_h, out_w, out, mm);
-  expand_normalize_kernel<<<(n + 255) / 256, 256, 0, stream>>>(out, n, mm, absolute, use_threshold, threshold);
-  DAAM_CUDA_TRY(cudaGetLastError());
-  count_launch(3);
-  return DAAM_OK;
+  static thread_local ExpandWordsParams p;
+  p.maps = global_maps; p.word_maps = word_maps; p.out = out; p.scratch = scratch;
+  p.x = x; p.oh = out_h; p.ow = out_w; p.n_words = n_words; p.chunks = 1;
+  p.absolute = absolute ? 1 : 0; p.use_threshold = use_threshold ? 1 : 0; p.threshold = threshold;
+  for (int w = 0; w < n_words; ++w) {
+    if (row_begin[w + 1] <= row_begin[w]) { set_error("daam_expand_words: word %d selects no row", w); return DAAM_E_INVALID; }
+    p.row_begin[w] = row_begin[w];
+  }
+  p.row_begin[n_words] = row_begin[n_words];
+  for (int i = 0; i < row_begin[n_words]; ++i) {
+    int r = rows[i];
+    if (r < 0) r += n_rows;   // torch-style negative index
+    if (r < 0 || r >= n_rows) { set_error("daam_expand_words: row %d out of range [0, %d)", rows[i], n_rows); return DAAM_E_INVALID; }
+    p.rows[i] = r;
+  }
+  return launch_expand_words(p, dev, stream);
+}
+
+extern "C" int daam_expand_as(const float* word_map, int32_t x, int32_t out_h, int32_t out_w, int32_t absolute,
+                              int32_t use_threshold, float threshold, float* out, float* scratch, void* stream_) {
+  // one word whose "rows" are the word map itself
+  const int32_t rows[1] = {0}, row_begin[2] = {0, 1};
+  if (!word_map) { set_error("daam_expand_as: null pointer or non-positive size"); return DAAM_E_INVALID; }
+  return daam_expand_words(word_map, 1, x, rows, row_begin, 1, out_h, out_w, absolute, use_threshold, threshold, nullptr,
+                           out, scratch, stream_);
 }

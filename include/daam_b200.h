@@ -49,6 +49,8 @@ enum daam_dtype { DAAM_F32 = 0, DAAM_F16 = 1, DAAM_BF16 = 2 };
 #define DAAM_ACC_RMW_LDST   0x10u /* coalesced load / add / store of the accumulator tile */
 #define DAAM_ACC_RMW_RED    0x20u /* red.global.add.f32 (SIMT) / bulk-async reduce-add from shared memory (MMA) */
 #define DAAM_ACC_NO_PDL     0x100u /* launch without programmatic dependent launch (measurement / debugging) */
+#define DAAM_ACC_RED_SEGMENTS 0x400u /* tcgen05 kernel, RED mode: 7 bulk-tensor reduce-adds of 11 token rows per tile */
+#define DAAM_ACC_RED_ROWS   0x800u /* tcgen05 kernel, RED mode: 77 one-row bulk reduce-adds per tile (one per thread) */
 #define DAAM_ACC_EARLY_LOADS 0x200u /* The caller vouches that q and k of every layer were complete BEFORE the previous
                                      kernel on `stream` started (they were produced on another stream and joined through
                                      an event, or are resident inputs). Then only the kernel's accumulator updates wait
@@ -149,10 +151,26 @@ int daam_word_heat_map(const float* global_maps, int32_t n_rows, int32_t x, cons
  * Replaces WordHeatMap.expand_as's tensor part (daam/heatmap.py:77-93): bicubic upsample of word_map [x][x] to
  * [out_h][out_w], then unless `absolute` (im - min) / (max - min + 1e-8), then if `use_threshold` binarise
  * (im > threshold) (the reference's `if threshold:` -- Python truthiness -- is resolved by the host).
- * out: device fp32 [out_h][out_w]; scratch: device, >= 2 floats (min/max), owned by the caller.
+ * out: device fp32 [out_h][out_w]; scratch: device, >= DAAM_EXPAND_SCRATCH_FLOATS floats, owned by the caller.
+ * One launch (the n_words = 1 case of daam_expand_words).
  */
+#define DAAM_EXPAND_SCRATCH_FLOATS 64   /* per word: partial min/max of up to 32 pixel chunks */
 int daam_expand_as(const float* word_map, int32_t x, int32_t out_h, int32_t out_w, int32_t absolute,
                    int32_t use_threshold, float threshold, float* out, float* scratch, void* stream);
+
+/*
+ * The per-word loop a user of the reference writes -- `for word in prompt: global_heat_map.compute_word_heat_map(word)
+ * .expand_as(image)` (daam/heatmap.py:121-123 then :77-93; e.g. daam/run/generate.py, the README example) -- for a LIST
+ * of words in one cooperative launch: word w averages rows[row_begin[w] .. row_begin[w+1]) of global_maps
+ * [n_rows][x][x] (rows already offset by +1 for SOS, daam/utils.py:91), the [x][x] mean is bicubic-upsampled to
+ * [out_h][out_w], min-max normalised unless `absolute`, binarised if `use_threshold`.
+ * out: device fp32 [n_words][out_h][out_w]; word_maps: optional device fp32 [n_words][x][x] (the word heat maps
+ * themselves, NULL to skip); scratch: device, >= DAAM_EXPAND_SCRATCH_FLOATS * n_words floats; rows / row_begin: host.
+ * Limits: n_words <= 96, row_begin[n_words] <= 320. Nothing is copied to the host: the caller reads `out` back once.
+ */
+int daam_expand_words(const float* global_maps, int32_t n_rows, int32_t x, const int32_t* rows, const int32_t* row_begin,
+                      int32_t n_words, int32_t out_h, int32_t out_w, int32_t absolute, int32_t use_threshold,
+                      float threshold, float* word_maps, float* out, float* scratch, void* stream);
 
 /* Library / device introspection. */
 int daam_abi_version(void);

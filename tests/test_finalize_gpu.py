@@ -177,3 +177,63 @@ def test_iou_ioa_match_the_reference_formulas():
     i2 = (up * big).sum()
     assert compute_iou(small.to(DEV), big.to(DEV)) == pytest.approx((i2 / (up.sum() + big.sum() - i2 + 1e-8)).item(), rel=2e-3)
     assert compute_ioa(small.to(DEV), big.to(DEV)) == pytest.approx((i2 / (up.sum() + 1e-8)).item(), rel=2e-3)
+
+
+def test_expand_words_fused_matches_reference_fixture_and_the_per_word_loop():
+    """daam_expand_words (one launch for a word list: row gather-mean -> bicubic to the image size -> min/max ->
+    normalise / threshold; daam/heatmap.py:121-123 + 77-93) against the verbatim reference's expand_as outputs and
+    against this package's own per-word compute_word_heat_map().expand_as() loop."""
+    fx = golden('finalize')
+    tok = WhitespaceTokenizer()
+    g = torch.from_numpy(fx['global']).to(DEV)
+    prompt = str(fx['prompt'])
+    ghm = GlobalHeatMap(tok, prompt, g)
+    img = SimpleNamespace(size=(96, 80))
+    words = prompt.split()
+    before = _native.launch_count()
+    whms, exp = ghm.expand_words(words, img)
+    assert _native.launch_count() - before == 1                       # one launch for the whole list
+    assert not exp.is_cuda and exp.shape == (len(words), 96, 80)
+    i3 = words.index('three')
+    assert rel_err(whms[i3].heatmap, fx['word_three']) < 1e-6 and whms[i3].word == 'three'
+    assert rel_err(exp[i3], fx['expand']) < 1e-5
+    _, exp_abs = ghm.expand_words(['three'], img, absolute=True)
+    assert rel_err(exp_abs[0], fx['expand_abs']) < 1e-5
+    _, exp_thr = ghm.expand_words(['three'], img, threshold=0.4)
+    assert (exp_thr[0].numpy() != fx['expand_thr']).mean() < 1e-3
+    for i, w in enumerate(words):                                       # == the per-word loop, bit for bit
+        single = ghm.compute_word_heat_map(w)
+        assert torch.equal(single.heatmap, whms[i].heatmap), w
+        assert torch.equal(single.expand_as(img), exp[i]), w
+    # multi-row words (two occurrences), explicit word indices, device-resident result, image-sized output
+    multi = GlobalHeatMap(tok, 'red ball and red car', g)
+    big = SimpleNamespace(size=(512, 512))
+    whm2, dev_out = multi.expand_words(['red', 'car', 'x'], big, word_idx=[None, None, 2], to_cpu=False)
+    assert dev_out.is_cuda and dev_out.shape == (3, 512, 512)
+    assert rel_err(whm2[0].heatmap, fx['word_red_multi']) < 1e-6
+    for i, (w, idx) in enumerate([('red', None), ('car', None), ('x', 2)]):
+        ref = multi.compute_word_heat_map(w, word_idx=idx).expand_as(big)
+        assert torch.equal(ref, dev_out[i].cpu()), w
+        assert float(dev_out[i].min()) == 0.0 and abs(float(dev_out[i].max()) - 1.0) < 1e-6
+    with pytest.raises(ValueError, match='Search word zebra not found in prompt!'):
+        ghm.expand_words(['one', 'zebra'], img)
+    assert ghm.expand_words([], img)[0] == []
+
+
+def test_expand_words_many_words_and_oracle():
+    """More (word, chunk) CTAs than one cooperative grid holds at the largest chunk count: the host batches; every word
+    against the oracle's port of compute_word_heat_map + expand_as."""
+    g = torch.Generator().manual_seed(4)
+    n_rows = 77
+    maps = torch.exp(torch.randn(n_rows, 64, 64, generator=g))
+    prompt = ' '.join(f'w{i}' for i in range(75))
+    tok = WhitespaceTokenizer()
+    ghm = GlobalHeatMap(tok, prompt, maps.to(DEV))
+    img = SimpleNamespace(size=(128, 96))
+    words = prompt.split()
+    whms, exp = ghm.expand_words(words, img)
+    assert exp.shape == (75, 128, 96)
+    for i in (0, 1, 37, 74):
+        ref_w = O.port_word_heat_map(maps, tok, prompt, words[i])
+        assert rel_err(whms[i].heatmap, ref_w) < 1e-6
+        assert rel_err(exp[i], O.port_expand_as(ref_w, (128, 96))) < 1e-5

@@ -56,6 +56,8 @@ def main():
         'mma-ldst': _native.ACC_FORCE_MMA | _native.ACC_RMW_LDST,
         'mma-red-nopdl': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED | _native.ACC_NO_PDL,
         'mma-red-early': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED | _native.ACC_EARLY_LOADS,
+        'mma-seg-early': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED | _native.ACC_EARLY_LOADS | _native.ACC_RED_SEGMENTS,
+        'mma-rows-early': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED | _native.ACC_EARLY_LOADS | _native.ACC_RED_ROWS,
     }
     if args.variants:
         variants = {k: v for k, v in variants.items() if k in args.variants}
@@ -81,7 +83,7 @@ def main():
             del sets
             torch.cuda.empty_cache()
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-    with open(os.path.join(ROOT, 'gpurun_out', f'microbench_{args.workload}.json'), 'w') as f:
+    with open(os.path.join(ROOT, 'gpurun_out', f'microbench_{args.workload}_{"-".join(args.dtypes)}.json'), 'w') as f:
         json.dump(rows, f, indent=1)
 
 
