@@ -17,14 +17,15 @@ DAAM_F32, DAAM_F16, DAAM_BF16 = 0, 1, 2
 ACC_AUTO, ACC_FORCE_SIMT, ACC_FORCE_MMA = 0, 1, 2
 ACC_RMW_AUTO, ACC_RMW_LDST, ACC_RMW_RED = 0x00, 0x10, 0x20
 ACC_NO_PDL = 0x100
-ACC_RED_SEGMENTS, ACC_RED_ROWS = 0x400, 0x800
+ACC_RED_SEGMENTS, ACC_RED_ROWS, ACC_RED_REGS = 0x400, 0x800, 0x1000
 ACC_EARLY_LOADS = 0x200   # see include/daam_b200.h: only valid when q/k were complete before the previous kernel started
 ABI_VERSION = 3
 E_INVALID, E_UNSUPPORTED, E_CUDA = -1, -2, -3
 TOKENS = 77
 EXPAND_SCRATCH_FLOATS = 64   # DAAM_EXPAND_SCRATCH_FLOATS: per word
 
-EXPORTS = ('daam_accumulate', 'daam_attention_probs', 'daam_accumulate_probs', 'daam_finalize', 'daam_finalize_per_key', 'daam_word_heat_map', 'daam_expand_as', 'daam_expand_words', 'daam_abi_version',
+EXPORTS = ('daam_accumulate', 'daam_attention_probs', 'daam_accumulate_probs', 'daam_finalize', 'daam_finalize_per_key', 'daam_word_heat_map', 'daam_expand_as', 'daam_expand_words', 'daam_side_launcher_create', 'daam_side_launcher_destroy',
+           'daam_side_launcher_launch', 'daam_side_launcher_join', 'daam_side_launcher_idle', 'daam_abi_version',
            'daam_last_error', 'daam_device_info', 'daam_launch_count')
 
 
@@ -90,6 +91,16 @@ def load() -> ctypes.CDLL:
     lib.daam_expand_words.argtypes = [vp, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), i32, i32, i32, i32, i32, f32,
                                       vp, vp, vp, vp]
     lib.daam_expand_words.restype = ctypes.c_int
+    lib.daam_side_launcher_create.argtypes = [ctypes.POINTER(vp)]
+    lib.daam_side_launcher_create.restype = ctypes.c_int
+    lib.daam_side_launcher_destroy.argtypes = [vp]
+    lib.daam_side_launcher_destroy.restype = None
+    lib.daam_side_launcher_launch.argtypes = [vp, ctypes.POINTER(DaamLayer), i32, u32, vp, vp]
+    lib.daam_side_launcher_launch.restype = ctypes.c_int
+    lib.daam_side_launcher_join.argtypes = [vp, vp]
+    lib.daam_side_launcher_join.restype = ctypes.c_int
+    lib.daam_side_launcher_idle.argtypes = [vp]
+    lib.daam_side_launcher_idle.restype = ctypes.c_int
     lib.daam_last_error.argtypes = []
     lib.daam_last_error.restype = ctypes.c_char_p
     lib.daam_device_info.argtypes = [ctypes.POINTER(i32)] * 3
@@ -111,6 +122,43 @@ class PackedLayers:
     def __init__(self, layers: Sequence[DaamLayer]):
         self.n = len(layers)
         self.array = (DaamLayer * max(self.n, 1))(*layers)
+
+
+class SideLauncher:
+    """``daam_side_launcher``: the event pair behind the tracer's per-step launch on its side stream."""
+
+    def __init__(self):
+        self._lib = load()
+        handle = ctypes.c_void_p()
+        _check(self._lib.daam_side_launcher_create(ctypes.byref(handle)))
+        self._h = handle
+
+    def launch(self, packed: 'PackedLayers', flags: int, producer_stream: int, side_stream: int):
+        rc = self._lib.daam_side_launcher_launch(self._h, packed.array, packed.n, flags, producer_stream, side_stream)
+        if rc != 0:
+            _check(rc)
+
+    def join(self, stream: int):
+        rc = self._lib.daam_side_launcher_join(self._h, stream)
+        if rc != 0:
+            _check(rc)
+
+    def idle(self) -> bool:
+        rc = self._lib.daam_side_launcher_idle(self._h)
+        if rc < 0:
+            _check(rc)
+        return rc == 1
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            self._lib.daam_side_launcher_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def accumulate(layers, stream: int, flags: int = ACC_AUTO):

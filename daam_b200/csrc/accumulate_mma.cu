@@ -31,6 +31,7 @@
 //
 // Replaces daam/trace.py:276 (get_attention_scores), :219-244 (_unravel_attn) and :293-294 (update loop).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -54,7 +55,7 @@ constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kPBytes + kBarBytes;
 // split (fp32) form: a raw stage holds the fp32 tiles as [Q sub0][Q sub1][K sub0][K sub1] (sub-tile = 32 floats = one
 // 128-byte swizzle span per row); one more buffer of the same shape holds the lo terms; warps 6-9 convert
 constexpr int kSplitStageBytes = 2 * kStageBytes;     // 53248 = 52 x 1024
-constexpr int kSplitThreads = 320;
+constexpr int kSplitThreads = 448;                   // launch bound; 192 + 32 x converter warps (4 or 8) at run time
 constexpr int kSplitSmemBytes = 1024 + (kStages + 1) * kSplitStageBytes + kPBytes + kBarBytes;
 static_assert(kSplitSmemBytes <= 232448, "split form exceeds the 227 KB shared-memory limit");
 
@@ -210,14 +211,20 @@ __device__ __forceinline__ float rna_tf32(float x) {
 // Converter warps (split form): a landed fp32 region [begin, end) of a raw stage (16-byte units, any swizzle -- the pass
 // is elementwise) is rewritten in place to hi = rna_tf32(x) and lo = rna_tf32(x - hi) goes to the same offsets of the lo
 // buffer. x - hi is exact in fp32 (|x - hi| <= half a tf32 ulp of x), so hi + lo carries 22 significand bits of x.
-__device__ __forceinline__ void split_region(uint8_t* raw, uint8_t* lo, int begin, int end, int ctid) {
+__device__ __forceinline__ void split_region(uint8_t* raw, uint8_t* lo, int begin, int end, int ctid, int n_conv,
+                                             bool write_hi) {
 #pragma unroll 4
-  for (int off = begin + ctid * 16; off < end; off += 128 * 16) {
+  for (int off = begin + ctid * 16; off < end; off += n_conv * 16) {
     float4 x = *reinterpret_cast<const float4*>(raw + off);
     float4 h, l;
-    h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
+    if (write_hi) {
+      h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
+      *reinterpret_cast<float4*>(raw + off) = h;
+    } else {   // EXPERIMENT: the tensor core truncates the container itself; lo = x - trunc(x)
+      h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+      h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+    }
     l.x = rna_tf32(x.x - h.x); l.y = rna_tf32(x.y - h.y); l.z = rna_tf32(x.z - h.z); l.w = rna_tf32(x.w - h.w);
-    *reinterpret_cast<float4*>(raw + off) = h;
     *reinterpret_cast<float4*>(lo + off) = l;
   }
 }
@@ -259,7 +266,7 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
       mbar_init(tfull0 + 8 * a, 1);
       mbar_init(tempty0 + 8 * a, 4);       // one arrival per epilogue warp
     }
-    mbar_init(lofull, 4);                  // one arrival per converter warp
+    mbar_init(lofull, kSplit ? (blockDim.x - 192) / 32 : 1);   // one arrival per converter warp
     mbar_init(loempty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -294,7 +301,8 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
 
   if (kSplit && warp >= 6) {
     // ===== converter warps (fp32 projections): landed fp32 tile -> hi (in place) + lo (second buffer) =====
-    const int ctid = threadIdx.x - 192;
+    const int ctid = threadIdx.x - 192, n_conv = blockDim.x - 192;
+    const bool write_hi = !(P.pad_ & 1);
     uint8_t* lo = gen + kStages * kStageBytesT;
     int li = 0, j = 0;
     for (int i = 0; i < count; ++i) {
@@ -307,8 +315,8 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
         mbar_wait(full0 + 8 * s, (uint32_t)(j / kStages) & 1u);         // TMA has landed the raw tiles
         mbar_wait(loempty, ((uint32_t)j & 1u) ^ 1u);                   // the MMAs of the previous chunk have read lo
         uint8_t* stage = gen + s * kStageBytesT;
-        split_region(stage, lo, 0, subs * kQBytes, ctid);
-        split_region(stage, lo, 2 * kQBytes, 2 * kQBytes + subs * kKBytes, ctid);
+        split_region(stage, lo, 0, subs * kQBytes, ctid, n_conv, write_hi);
+        split_region(stage, lo, 2 * kQBytes, 2 * kQBytes + subs * kKBytes, ctid, n_conv, write_hi);
         fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core's reads
         __syncwarp();
         if (lane == 0) mbar_arrive(lofull);
@@ -475,6 +483,17 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
           bulk_commit();
         }
         issued = true;
+      } else if (P.rmw_mode == 4) {
+        // register reds: red.global.add.f32 straight from the softmax registers, one 128-byte coalesced reduction per
+        // warp and token; fire-and-forget (no staging buffer, nothing to wait for before the next tile)
+        const int pixel = t.pixel0 + tid;
+        if (pixel < L.hw) {
+          const long long hw = L.hw;
+          float* acc = L.acc + ((long long)(t.prompt * L.heads + t.head) * kTokens) * hw + pixel;
+#pragma unroll
+          for (int j = 0; j < kTokens; ++j)
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(acc + j * hw), "f"(v[j] * inv) : "memory");
+        }
       } else {
         const int pixel = t.pixel0 + tid;
         if (pixel < L.hw) {
@@ -642,16 +661,23 @@ int prepare_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, void* o
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
       if (e != cudaSuccess) attr_err = e;
     };
-    set((const void*)accumulate_mma_kernel<false, false>, kSmemBytes);
-    set((const void*)accumulate_mma_kernel<false, true>, kSmemBytes);
+    set((const void*)accumulate_mma_kernel<false, false>, 120 * 1024);
+    set((const void*)accumulate_mma_kernel<false, true>, 120 * 1024);
     set((const void*)accumulate_mma_kernel<true, false>, kSplitSmemBytes);
     set((const void*)accumulate_mma_kernel<true, true>, kSplitSmemBytes);
   });
   DAAM_CUDA_TRY(attr_err);
-  pm.grid = dev.sm_count * (split ? 1 : 2);
+  // EXPERIMENT knobs (environment, read per prepare): converter warps, hi rewrite, one 16-bit CTA per SM
+  const char* e_conv = getenv("DAAM_SPLIT_CONV_WARPS");
+  const char* e_nohi = getenv("DAAM_SPLIT_NO_HI");
+  const char* e_one = getenv("DAAM_MMA_ONE_CTA");
+  const int conv_warps = e_conv && e_conv[0] == '8' ? 8 : 4;
+  if (e_nohi && e_nohi[0] == '1') mp.base.pad_ |= 1;
+  const bool one_cta = !split && e_one && e_one[0] == '1';
+  pm.grid = dev.sm_count * (split || one_cta ? 1 : 2);
   if (pm.grid > p.total_tiles) pm.grid = p.total_tiles;
-  pm.block = split ? kSplitThreads : kThreads;
-  pm.smem = split ? kSplitSmemBytes : kSmemBytes;
+  pm.block = split ? 192 + 32 * conv_warps : kThreads;
+  pm.smem = split ? kSplitSmemBytes : one_cta ? 120 * 1024 : kSmemBytes;
   pm.variant = (split ? 1 : 0) | (chunked ? 2 : 0);
   return DAAM_OK;
 }

@@ -114,7 +114,7 @@ int build_plan(const daam_layer* layers, int n_layers, uint32_t flags, const Dev
   LaunchParams packs[3];                 // 0: tcgen05 16-bit, 1: tcgen05 fp32, 2: SIMT
   for (LaunchParams& p : packs) {
     p.n_layers = p.total_tiles = 0;
-    p.rmw_mode = (rmw == DAAM_ACC_RMW_LDST) ? 0 : (flags & DAAM_ACC_RED_ROWS) ? 3 : (flags & DAAM_ACC_RED_SEGMENTS) ? 2 : 1;
+    p.rmw_mode = (rmw == DAAM_ACC_RMW_LDST) ? 0 : (flags & DAAM_ACC_RED_REGS) ? 4 : (flags & DAAM_ACC_RED_ROWS) ? 3 : (flags & DAAM_ACC_RED_SEGMENTS) ? 2 : 1;
     p.pdl = (flags & DAAM_ACC_NO_PDL) ? 0 : 1;
     p.early_loads = (flags & DAAM_ACC_EARLY_LOADS) && p.pdl ? 1 : 0;
     p.pad_ = 0;
@@ -201,6 +201,62 @@ extern "C" int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint3
     if (rc) return rc;
   }
   return DAAM_OK;
+}
+
+// ---- side-stream launcher ------------------------------------------------------------------------------------------
+struct daam_side_launcher {
+  cudaEvent_t ready = nullptr, done = nullptr;
+  int device = -1;
+  bool launched = false;
+};
+
+extern "C" int daam_side_launcher_create(daam_side_launcher** out) {
+  if (!out) { set_error("daam_side_launcher_create: null pointer"); return DAAM_E_INVALID; }
+  DeviceInfo dev;
+  if (int rc = get_device_info(&dev)) return rc;
+  std::unique_ptr<daam_side_launcher> h(new daam_side_launcher);
+  h->device = dev.device;
+  DAAM_CUDA_TRY(cudaEventCreateWithFlags(&h->ready, cudaEventDisableTiming));
+  if (cudaError_t e = cudaEventCreateWithFlags(&h->done, cudaEventDisableTiming)) {
+    cudaEventDestroy(h->ready);
+    return cuda_fail(e, "cudaEventCreateWithFlags");
+  }
+  *out = h.release();
+  return DAAM_OK;
+}
+
+extern "C" void daam_side_launcher_destroy(daam_side_launcher* h) {
+  if (!h) return;
+  if (h->ready) cudaEventDestroy(h->ready);
+  if (h->done) cudaEventDestroy(h->done);
+  delete h;
+}
+
+extern "C" int daam_side_launcher_launch(daam_side_launcher* h, const daam_layer* layers, int32_t n_layers, uint32_t flags,
+                                         void* producer_stream, void* side_stream) {
+  if (!h) { set_error("daam_side_launcher_launch: null launcher"); return DAAM_E_INVALID; }
+  cudaStream_t producer = static_cast<cudaStream_t>(producer_stream), side = static_cast<cudaStream_t>(side_stream);
+  DAAM_CUDA_TRY(cudaEventRecord(h->ready, producer));          // the projections were produced on `producer`
+  DAAM_CUDA_TRY(cudaStreamWaitEvent(side, h->ready, 0));
+  if (int rc = daam_accumulate(layers, n_layers, flags, side_stream)) return rc;
+  DAAM_CUDA_TRY(cudaEventRecord(h->done, side));
+  h->launched = true;
+  return DAAM_OK;
+}
+
+extern "C" int daam_side_launcher_join(daam_side_launcher* h, void* stream) {
+  if (!h) { set_error("daam_side_launcher_join: null launcher"); return DAAM_E_INVALID; }
+  if (h->launched) DAAM_CUDA_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->done, 0));
+  return DAAM_OK;
+}
+
+extern "C" int daam_side_launcher_idle(daam_side_launcher* h) {
+  if (!h) { set_error("daam_side_launcher_idle: null launcher"); return DAAM_E_INVALID; }
+  if (!h->launched) return 1;
+  const cudaError_t e = cudaEventQuery(h->done);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) return 0;
+  return cuda_fail(e, "cudaEventQuery");
 }
 
 extern "C" int daam_abi_version(void) { return DAAM_ABI_VERSION; }

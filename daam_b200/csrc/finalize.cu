@@ -130,26 +130,6 @@ struct PhaseWeights {
   }
 };
 
-// Fills keys[] (shared) with the source pointer (token row t) of every selected key of the class; returns the count.
-__device__ __forceinline__ int stage_class_keys(const FinalizeParams& P, int cls_side, int t, const float** keys) {
-  __shared__ int n_keys_s;
-  __syncthreads();                                     // the previous class is done with keys[]
-  if (threadIdx.x == 0) {
-    int n = 0;
-    for (int g = 0; g < P.n_groups; ++g) {
-      const daam_key_group& G = P.g[g];
-      if (G.h != cls_side || G.w != cls_side) continue;
-      const int h0 = G.head_sel < 0 ? 0 : G.head_sel;
-      const int h1 = G.head_sel < 0 ? G.heads : G.head_sel + 1;
-      const long long hw = (long long)G.h * G.w;
-      for (int head = h0; head < h1; ++head) keys[n++] = G.acc + ((long long)head * G.tokens + t) * hw;
-    }
-    n_keys_s = n;
-  }
-  __syncthreads();
-  return n_keys_s;
-}
-
 template <int F>
 __device__ __forceinline__ void add_key(const PhaseWeights<F>& pw, const float (&v)[5][5], float (&acc)[F][F]) {
   float r[5][F];                                       // horizontal pass, per source row and output phase
@@ -184,121 +164,37 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int F>
-__device__ __forceinline__ void class_pass(const FinalizeParams& P, int side, int t, int band, int br, float* tile,
-                                           const float** keys, float* stage) {
-  const int x = P.x;
-  const int R = br / F;                                // source rows under this band
-  const int VR = R + 4;                                // + 2 halo rows above and below
-  const int region = VR * side;                        // floats of one key's staged rows
-  const int n_src = R * side;                          // source pixels under the band (<= 256, checked by the host)
-  const int kg = 256 / n_src;                          // thread groups that split the keys
-  int kc = kStageFloats / region;                      // keys per chunk, a multiple of kg so every group keeps its stride
-  kc -= kc % kg;
-  const int nk = stage_class_keys(P, side, t, keys);
-  const int n_chunks = (nk + kc - 1) / kc;
-  const int row_units = side / 4, key_units = VR * row_units;     // 16-byte units
-  const int sy0 = band * R;
-
-  auto issue = [&](int c) {
-    float* buf = stage + (c & 1) * kStageFloats;
-    const int k0 = c * kc, kn = min(kc, nk - k0);
-    for (int u = threadIdx.x; u < kn * key_units; u += blockDim.x) {
-      const int k = u / key_units, rem = u - k * key_units;
-      const int vr = rem / row_units, c4 = rem - vr * row_units;
-      const int row = min(max(sy0 - 2 + vr, 0), side - 1);          // border rows are replicated, as the taps clamp
-      cp_async16(buf + k * region + vr * side + 4 * c4, keys[k0 + k] + row * side + 4 * c4);
-    }
-    cp_async_commit();
-  };
-
-  const int group = (int)threadIdx.x / n_src;
-  const int s = (int)threadIdx.x - group * n_src;
-  const bool live = group < kg;
-  const int ly = s / side, sx = s - ly * side;
-  int ix[5];
-#pragma unroll
-  for (int j = 0; j < 5; ++j) ix[j] = min(max(sx - 2 + j, 0), side - 1);
-  PhaseWeights<F> pw;
-  pw.init();
-  float acc[F][F];
-#pragma unroll
-  for (int py = 0; py < F; ++py)
-#pragma unroll
-    for (int px = 0; px < F; ++px) acc[py][px] = 0.f;
-
-  if (n_chunks > 0) issue(0);
-  for (int c = 0; c < n_chunks; ++c) {
-    if (c + 1 < n_chunks) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();                                   // chunk c has landed for every thread
-    if (live) {
-      const float* buf = stage + (c & 1) * kStageFloats + ly * side;
-      const int kn = min(kc, nk - c * kc);
-      for (int k = group; k < kn; k += kg) {
-        const float* src = buf + k * region;
-        float v[5][5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i)
-#pragma unroll
-          for (int j = 0; j < 5; ++j) v[i][j] = src[i * side + ix[j]];
-        add_key<F>(pw, v, acc);
-      }
-    }
-    __syncthreads();                                   // buffer (c & 1) may be overwritten by chunk c + 2
-  }
-  for (int g = 0; g < kg; ++g) {                       // merge the key groups in a fixed order
-    if (live && group == g) {
-      const int oy0 = ly * F, ox0 = sx * F;
-#pragma unroll
-      for (int py = 0; py < F; ++py)
-#pragma unroll
-        for (int px = 0; px < F; ++px) tile[(oy0 + py) * x + ox0 + px] += acc[py][px];
-    }
-    __syncthreads();
-  }
-}
-
-// factor 1: bicubic at scale 1 is the identity, the class contributes clamp(src) -- coalesced float4 reads; when the
-// band has fewer float4s than threads, the spare thread groups take every kg-th key (merged in a fixed order)
-__device__ __forceinline__ void class_pass_identity(const FinalizeParams& P, int t, int band, int br, float* tile,
-                                                    const float** keys) {
-  const int x = P.x;
-  const int n4 = br * x / 4;
-  const int nk = stage_class_keys(P, x, t, keys);
-  const int kg = n4 >= 256 ? 1 : 256 / n4;
-  const int passes = (n4 + 255) / 256;
-  for (int pass = 0; pass < passes; ++pass) {
-    const int group = n4 >= 256 ? 0 : (int)threadIdx.x / n4;
-    const int i = n4 >= 256 ? pass * 256 + (int)threadIdx.x : (int)threadIdx.x % n4;
-    const bool live = i < n4 && group < kg;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-      const long long off = (long long)band * br * x + 4 * i;
-#pragma unroll 8
-      for (int k = group; k < nk; k += kg) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(keys[k] + off));
-        acc.x += fmaxf(v.x, 0.f); acc.y += fmaxf(v.y, 0.f); acc.z += fmaxf(v.z, 0.f); acc.w += fmaxf(v.w, 0.f);
-      }
-    }
-    for (int g = 0; g < kg; ++g) {
-      if (live && group == g) {
-        float4* dst = reinterpret_cast<float4*>(tile + 4 * i);
-        float4 cur = *dst;
-        cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
-        *dst = cur;
-      }
-      __syncthreads();
-    }
-  }
-}
-
 struct ClassList {
   int n;
-  int band_rows;    // 8, or 4 when that is what fills the machine / keeps a band's source pixels within one CTA
-  int side[8];      // distinct source sides, all dividing x with factor 1, 2 or 4
+  int band_rows;            // 8, or 4 when that is what fills the machine / keeps a band's source pixels within one CTA
+  int side[8];              // distinct source sides, all dividing x with factor 1, 2 or 4
+  int key_begin[9];         // keys[] is ordered class by class: class c owns [key_begin[c], key_begin[c + 1])
+  int key_slot[kMaxGroups]; // where group g's first selected key goes in keys[]
 };
 
-// grid: (x / band_rows bands, n_rows); dynamic smem: band tile (band_rows * x floats) + two chunk buffers
+// Geometry of one class for a band of `br` output rows (all derived from side and x; a handful of integer ops).
+struct ClassGeom {
+  int side, f, rows, region, n_src, kg, kc, n_keys, key0, n_chunks, row_units;
+  __device__ __forceinline__ ClassGeom(const ClassList& C, int c, int x, int br) {
+    side = C.side[c];
+    f = x / side;
+    const int r = br / f;                              // source rows under the band
+    rows = f == 1 ? r : r + 4;                         // staged rows: + 2 halo rows above and below for the cubic taps
+    region = rows * side;                              // floats of one key's staged rows
+    n_src = f == 1 ? r * side / 4 : r * side;          // work items of the band: float4s (identity) or source pixels
+    kg = 256 / n_src;                                  // thread groups that split the keys (n_src <= 256, host-checked)
+    kc = kStageFloats / region;
+    kc -= kc % kg;                                     // keys per chunk: a multiple of kg, so every group keeps its stride
+    key0 = C.key_begin[c];
+    n_keys = C.key_begin[c + 1] - key0;
+    n_chunks = (n_keys + kc - 1) / kc;
+    row_units = side / 4;                              // 16-byte units per staged row
+  }
+};
+
+// grid: (x / band_rows bands, n_rows); dynamic smem: two chunk buffers + the band tile (band_rows * x floats).
+// The chunks of ALL classes form one double-buffered cp.async stream (the first chunk of the next class is in flight
+// while the last chunk of the current one is being reduced), so only the very first chunk's latency is exposed.
 __global__ void __launch_bounds__(256, 2) finalize_fast_kernel(const __grid_constant__ FinalizeParams P,
                                                                const __grid_constant__ ClassList C,
                                                                float* __restrict__ out) {
@@ -307,14 +203,121 @@ __global__ void __launch_bounds__(256, 2) finalize_fast_kernel(const __grid_cons
   float* stage = dyn;                                  // 2 x kStageFloats
   float* tile = dyn + 2 * kStageFloats;
   const int band = blockIdx.x, t = blockIdx.y, x = P.x, br = C.band_rows;
-  for (int i = threadIdx.x; i < br * x; i += blockDim.x) tile[i] = 0.f;
-  for (int c = 0; c < C.n; ++c) {
-    const int side = C.side[c], f = x / side;
-    if (f == 1) class_pass_identity(P, t, band, br, tile, keys);
-    else if (f == 2) class_pass<2>(P, side, t, band, br, tile, keys, stage);
-    else class_pass<4>(P, side, t, band, br, tile, keys, stage);
+  // key pointers (token row t) of every selected key, class by class; one thread per key group
+  for (int g = threadIdx.x; g < P.n_groups; g += blockDim.x) {
+    const daam_key_group& G = P.g[g];
+    const int h0 = G.head_sel < 0 ? 0 : G.head_sel;
+    const int h1 = G.head_sel < 0 ? G.heads : G.head_sel + 1;
+    const long long hw = (long long)G.h * G.w;
+    for (int head = h0; head < h1; ++head) keys[C.key_slot[g] + head - h0] = G.acc + ((long long)head * G.tokens + t) * hw;
   }
+  for (int i = threadIdx.x; i < br * x; i += blockDim.x) tile[i] = 0.f;
   __syncthreads();
+
+  auto issue = [&](int c, int q, int buf_idx) {
+    const ClassGeom G(C, c, x, br);
+    float* buf = stage + buf_idx * kStageFloats;
+    const int k0 = q * G.kc, kn = min(G.kc, G.n_keys - k0);
+    const int key_units = G.rows * G.row_units;
+    const int sy0 = band * (br / G.f) - (G.f == 1 ? 0 : 2);
+    for (int u = threadIdx.x; u < kn * key_units; u += blockDim.x) {
+      const int k = u / key_units, rem = u - k * key_units;
+      const int vr = rem / G.row_units, c4 = rem - vr * G.row_units;
+      const int row = min(max(sy0 + vr, 0), G.side - 1);            // border rows are replicated, as the taps clamp
+      cp_async16(buf + k * G.region + vr * G.side + 4 * c4, keys[G.key0 + k0 + k] + row * G.side + 4 * c4);
+    }
+    cp_async_commit();
+  };
+
+  float acc[16];
+  int c = 0, q = 0, it = 0;
+  issue(0, 0, 0);                                      // class 0 is never empty (host)
+  while (c < C.n) {
+    const ClassGeom G(C, c, x, br);
+    int nc = c, nq = q + 1;                            // the chunk after this one, possibly in the next class
+    if (nq == G.n_chunks) { nc = c + 1; nq = 0; }
+    if (nc < C.n) { issue(nc, nq, (it + 1) & 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();                                   // chunk (c, q) has landed for every thread
+
+    const int group = (int)threadIdx.x / G.n_src;
+    const int s = (int)threadIdx.x - group * G.n_src;
+    const bool live = group < G.kg;
+    if (q == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    }
+    const float* buf = stage + (it & 1) * kStageFloats;
+    const int kn = min(G.kc, G.n_keys - q * G.kc);
+    if (live) {
+      if (G.f == 1) {
+        for (int k = group; k < kn; k += G.kg) {
+          const float4 v = *reinterpret_cast<const float4*>(buf + k * G.region + 4 * s);
+          acc[0] += fmaxf(v.x, 0.f); acc[1] += fmaxf(v.y, 0.f); acc[2] += fmaxf(v.z, 0.f); acc[3] += fmaxf(v.w, 0.f);
+        }
+      } else {
+        const int ly = s / G.side, sx = s - ly * G.side;
+        int ix[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) ix[j] = min(max(sx - 2 + j, 0), G.side - 1);
+        const float* base = buf + ly * G.side;
+        if (G.f == 2) {
+          PhaseWeights<2> pw;
+          pw.init();
+          float (&a2)[2][2] = *reinterpret_cast<float (*)[2][2]>(acc);
+          for (int k = group; k < kn; k += G.kg) {
+            float v[5][5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+              for (int j = 0; j < 5; ++j) v[i][j] = base[k * G.region + i * G.side + ix[j]];
+            add_key<2>(pw, v, a2);
+          }
+        } else {
+          PhaseWeights<4> pw;
+          pw.init();
+          float (&a4)[4][4] = *reinterpret_cast<float (*)[4][4]>(acc);
+          for (int k = group; k < kn; k += G.kg) {
+            float v[5][5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+              for (int j = 0; j < 5; ++j) v[i][j] = base[k * G.region + i * G.side + ix[j]];
+            add_key<4>(pw, v, a4);
+          }
+        }
+      }
+    }
+    __syncthreads();                                   // buffer (it & 1) may be overwritten by the chunk after next
+    if (q + 1 == G.n_chunks) {
+      // end of the class: merge the key groups into the band tile in a fixed order (deterministic sums)
+      for (int g = 0; g < G.kg; ++g) {
+        if (live && group == g) {
+          if (G.f == 1) {
+            float4* dst = reinterpret_cast<float4*>(tile + 4 * s);
+            float4 cur = *dst;
+            cur.x += acc[0]; cur.y += acc[1]; cur.z += acc[2]; cur.w += acc[3];
+            *dst = cur;
+          } else {
+            const int ly = s / G.side, sx = s - ly * G.side;
+            const int oy0 = ly * G.f, ox0 = sx * G.f;
+            if (G.f == 2) {
+#pragma unroll
+              for (int py = 0; py < 2; ++py)
+#pragma unroll
+                for (int px = 0; px < 2; ++px) tile[(oy0 + py) * x + ox0 + px] += acc[py * 2 + px];
+            } else {
+#pragma unroll
+              for (int py = 0; py < 4; ++py)
+#pragma unroll
+                for (int px = 0; px < 4; ++px) tile[(oy0 + py) * x + ox0 + px] += acc[py * 4 + px];
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    c = nc; q = nq; ++it;
+  }
   float* dst = out + (long long)t * x * x + (long long)band * br * x;
   for (int i = threadIdx.x; i < br * x; i += blockDim.x) dst[i] = tile[i] / (float)P.n_keys;
 }
@@ -517,6 +520,16 @@ extern "C" int daam_finalize(const daam_key_group* groups, int32_t n_groups, int
     // 8-row bands unless that leaves the machine under-filled (< 2 CTAs per SM) or a band's source pixels of the
     // factor-2 class would exceed one CTA's 256 threads (x > 128)
     cls.band_rows = ((x / 8) * n_rows >= 2 * dev.sm_count && x <= 128) ? 8 : 4;
+    int next = 0;
+    for (int c = 0; c < cls.n; ++c) {                   // keys[] of the kernel: class by class, groups in call order
+      cls.key_begin[c] = next;
+      for (int i = 0; i < n_groups; ++i)
+        if (groups[i].h == cls.side[c]) {
+          cls.key_slot[i] = next;
+          next += groups[i].head_sel < 0 ? groups[i].heads : 1;
+        }
+    }
+    cls.key_begin[cls.n] = next;
     const size_t smem = (2 * kStageFloats + (size_t)cls.band_rows * x) * sizeof(float);
     static std::once_flag attr_once[64];
     cudaError_t attr_err = cudaSuccess;

@@ -32,13 +32,22 @@ def pad_heat_map(maps: torch.Tensor, tokens: int = TOKENS) -> torch.Tensor:
 
 
 def gather_heat_maps(local_maps: Sequence[torch.Tensor], n_total: int, x: int, group=None,
-                     tokens: int = TOKENS) -> Optional[torch.Tensor]:
+                     tokens: int = TOKENS, device=None) -> Optional[torch.Tensor]:
     """All-gathers per-prompt global heat maps. ``local_maps[j]`` belongs to prompt ``rank + j * world``; returns
-    ``[n_total, tokens, x, x]`` (rows beyond a prompt's length are zero) on every rank."""
+    ``[n_total, tokens, x, x]`` (rows beyond a prompt's length are zero) on every rank.
+
+    ``device``: where the exchange buffers live. Default: the device of ``local_maps``; a rank that owns no prompt
+    (``n_total < world``, or an uneven shard) has no map to infer it from and then uses the current CUDA device under
+    NCCL (every rank of a NCCL collective must pass CUDA tensors) and the CPU under gloo."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
     per_rank = (n_total + world - 1) // world
-    device = local_maps[0].device if local_maps else torch.device('cpu')
+    if device is None:
+        if local_maps:
+            device = local_maps[0].device
+        elif dist.is_initialized() and dist.get_backend(group) == 'nccl':
+            device = torch.device('cuda', torch.cuda.current_device())
+        else:
+            device = torch.device('cpu')
     mine = torch.zeros((per_rank, tokens, x, x), dtype=torch.float32, device=device)
     for j, m in enumerate(local_maps):
         mine[j] = pad_heat_map(m.float(), tokens)

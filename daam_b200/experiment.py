@@ -2,9 +2,11 @@
 
 A reduced mirror of the reference's ``GenerationExperiment`` (``/root/reference/daam/experiment.py:102-344``): the same
 fields and the same folder layout -- ``<path>/<id>/<subtype>/generation.pt`` (the pickled dataclass), ``output.png``,
-``<path>/<id>/prompt.txt``, ``seed.txt``, ``annotations.json`` (experiment.py:140-175) -- so that dumps written by either
-package load in the other (``load`` maps the reference's pickled class path ``daam.experiment.GenerationExperiment``
-onto this class). The COCO label tables, ground-truth / prediction mask handling and matplotlib heat-map rendering of
+``<path>/<id>/prompt.txt``, ``seed.txt``, ``annotations.json`` (experiment.py:140-175). Compatibility is ONE-WAY: dumps
+written by the reference load here (``load`` maps its pickled class path ``daam.experiment.GenerationExperiment`` onto
+this class); ``generation.pt`` written here pickles ``daam_b200.experiment.GenerationExperiment`` and is for this
+package (the text/PNG side files are identical either way). ``save`` moves the heat map to the CPU so that a dump loads
+on a box without a GPU. The COCO label tables, ground-truth / prediction mask handling and matplotlib heat-map rendering of
 the reference are out of scope.
 """
 from __future__ import annotations
@@ -74,7 +76,12 @@ class GenerationExperiment:
         matplotlib and is not part of the hot path."""
         root = self.path if path is None else Path(path) / self.id
         (root / self.subtype).mkdir(parents=True, exist_ok=True)
-        torch.save(self, root / self.subtype / 'generation.pt')
+        import copy
+        on_disk = self
+        if torch.is_tensor(self.global_heat_map) and self.global_heat_map.is_cuda:
+            on_disk = copy.copy(self)               # (not dataclasses.replace: __post_init__ would re-append the id)
+            on_disk.global_heat_map = self.global_heat_map.detach().cpu()
+        torch.save(on_disk, root / self.subtype / 'generation.pt')
         if hasattr(self.image, 'save'):                 # a PIL image
             self.image.save(root / self.subtype / 'output.png')
         (root / 'prompt.txt').write_text(self.prompt)

@@ -65,6 +65,7 @@ class RawHeatMapCollection:
     def __init__(self):
         self.slabs: Dict[int, LayerSlab] = {}
         self._order: List[int] = []          # layer indices in first-update order (the reference's dict order)
+        self.epoch = 0                        # bumped whenever a slab object is (re)allocated (descriptor caches key on it)
         self._sync = None                     # callable making pending kernel work visible to the current stream
         self._zero = None                     # callable(slabs) zeroing slabs in accumulate-stream order
 
@@ -89,6 +90,7 @@ class RawHeatMapCollection:
             acc = torch.zeros(shape, dtype=torch.float32, device=device)
             slab = LayerSlab(layer_idx, factor, heads, h, w, acc, head_offset=head_offset)
             self.slabs[layer_idx] = slab
+            self.epoch += 1
         if not slab.touched:
             slab.touched = True
             self._order.append(layer_idx)
@@ -115,6 +117,7 @@ class RawHeatMapCollection:
                 acc[:, :old.heads] = old.acc[:1]
             new = LayerSlab(layer_idx, factor, heads, h, w, acc, touched=True)
             self.slabs[layer_idx] = new
+            self.epoch += 1
             if layer_idx not in self._order:
                 self._order.append(layer_idx)
             slab = new

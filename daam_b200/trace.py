@@ -62,11 +62,19 @@ class DiffusionHeatMapHooker(AggregateHooker):
         self.launch = launch
         self.batch_prompts = batch_prompts
         self.kernel_flags = kernel_flags
-        self._pending: List[tuple] = []        # (layer_idx, DaamLayer, q, k, acc) awaiting the step launch
-        self._pending_layers = set()
-        self._desc_cache: Dict[int, tuple] = {}
-        self._packed = None                    # reusable host-side daam_layer[] for the step launch
-        self._inflight: List[tuple] = []       # (event, projections) of step launches that may still be running
+        # step queue: the layer calls of the running UNet forward, kept as one reusable host-side daam_layer[] whose slots
+        # are rewritten in place (in the steady state a layer only stores two pointers into its slot)
+        self._packed = _native.PackedLayers([_native.DaamLayer()] * 64)
+        self._slots = [self._packed.array[i] for i in range(64)]      # ctypes proxies into the array, created once
+        self._n_pending = 0
+        self._refs: List[torch.Tensor] = []    # the queued projections, kept alive until their launch has run
+        self._parked: List[list] = []          # projections of launches that may still be running
+        self._layer_state: Dict[int, tuple] = {}   # layer -> (q shape, dtype, position, slot, slab, q_off, k_off, device, own)
+        self._queued: Dict[int, int] = {}      # layer -> id of the step it was last queued in
+        self._step_id = 1
+        self._epoch_seen = -1                  # RawHeatMapCollection.epoch the cached layer states belong to
+        self._device = None
+        self._launcher: Optional[_native.SideLauncher] = None
         self._stream: Optional[torch.cuda.Stream] = None
         self._dirty = False                    # side-stream work not yet ordered before the current stream
         self.all_heat_maps.bind(self.synchronize, self._zero_slabs)
@@ -125,101 +133,161 @@ class DiffusionHeatMapHooker(AggregateHooker):
         """Register one traced layer call: ``q [B, hw, C]``, ``k [B, 77, C]`` straight from ``to_q`` / ``to_k``.
 
         This runs once per layer per step on the host's critical path, so the steady state does as little as possible:
-        when the projections are contiguous and shaped like the layer's previous call, only the two data pointers of
-        the cached ``daam_layer`` change."""
-        if layer_idx in self._pending_layers:   # the layer comes round again: a new UNet forward has started
+        when the projections are contiguous, shaped like the layer's previous call and the layer arrives at the same
+        position of the step as last time, only the two data pointers of its slot in the step's ``daam_layer[]`` change."""
+        if self._queued.get(layer_idx) == self._step_id:   # the layer comes round again: a new UNet forward has started
             self.flush()
-        cached = self._desc_cache.get(layer_idx)
-        if cached is not None and q.shape == cached[0] and q.dtype is cached[1] and q.is_contiguous() \
-                and k.is_contiguous() and self.all_heat_maps.slabs.get(layer_idx) is cached[3] \
-                and q.device == cached[3].acc.device:
-            _, _, desc, slab, q_off, k_off = cached
-            desc.q = q.data_ptr() + q_off
-            desc.k = k.data_ptr() + k_off
+        heat_maps = self.all_heat_maps
+        if heat_maps.epoch != self._epoch_seen:            # a slab was (re)allocated: cached descriptors may be stale
+            self._layer_state.clear()
+            self._epoch_seen = heat_maps.epoch
+        pos = self._n_pending if self.launch == 'step' else 0
+        st = self._layer_state.get(layer_idx)
+        if st is not None and q.shape == st[0] and q.dtype is st[1] and st[2] == pos and q.is_contiguous() \
+                and k.is_contiguous() and q.get_device() == st[7]:
+            slot, slab = st[3], st[4]
+            slot.q = q.data_ptr() + st[5]
+            slot.k = k.data_ptr() + st[6]
             if not slab.touched:
-                self.all_heat_maps.mark_live(slab)
+                heat_maps.mark_live(slab)
         else:
-            if not q.is_cuda:
-                raise RuntimeError('daam_b200 traces pipelines that live on a CUDA device only (there is no CPU '
-                                   'fallback)')
-            if q.stride(-1) != 1 or k.stride(-1) != 1:
-                q, k = q.contiguous(), k.contiguous()
-            bsz, hw, _ = q.shape
-            side = int(math.sqrt(hw))
-            if side * side != hw:
-                raise RuntimeError(f'layer {layer_idx}: {hw} query positions are not a square map')
-            # "second half of the batch*heads axis" (trace.py:240): the conditional samples of a CFG batch
-            _, n_prompts, head0, n_heads = ops.cond_half(bsz, heads)
-            if n_prompts > 1 and not self.batch_prompts:
-                raise ValueError('Only single prompt generation is supported for heat map computation.')
-            slab = self.all_heat_maps.slab_for(layer_idx, factor, n_prompts, n_heads, side, side, q.device, head0)
-            desc = ops.make_layer_desc(q, k, slab.acc, heads, scale)
-            # the fast path above is only valid for contiguous projections (strides implied by the shape)
-            shape_key = q.shape if (q.is_contiguous() and k.is_contiguous()) else None
-            self._desc_cache[layer_idx] = (shape_key, q.dtype, desc, slab, desc.q - q.data_ptr(), desc.k - k.data_ptr())
+            st = self._describe(layer_idx, factor, q, k, heads, scale, pos)
+            slab = st[4]
         if self.launch == 'layer':
             if torch.cuda.is_current_stream_capturing():
                 slab.captured = True
-            ops.accumulate([desc], q.device, flags=self.kernel_flags)
+            self._launch_now(st[8], q.device)
             return
-        self._pending.append((layer_idx, desc, q, k, slab))   # tensors kept alive until the launch
-        self._pending_layers.add(layer_idx)
+        self._refs.append(q)                               # kept alive until the step's launch has run
+        self._refs.append(k)
+        self._queued[layer_idx] = self._step_id
+        self._n_pending = pos + 1
+
+    def _describe(self, layer_idx: int, factor: int, q: torch.Tensor, k: torch.Tensor, heads: int, scale: float, pos: int):
+        """Slow path of :meth:`_enqueue`: (re)build the layer's slab and descriptor and cache them."""
+        if not q.is_cuda:
+            raise RuntimeError('daam_b200 traces pipelines that live on a CUDA device only (there is no CPU '
+                               'fallback)')
+        if q.stride(-1) != 1 or k.stride(-1) != 1:
+            q, k = q.contiguous(), k.contiguous()
+        bsz, hw, _ = q.shape
+        side = int(math.sqrt(hw))
+        if side * side != hw:
+            raise RuntimeError(f'layer {layer_idx}: {hw} query positions are not a square map')
+        # "second half of the batch*heads axis" (trace.py:240): the conditional samples of a CFG batch
+        _, n_samples, head0, n_heads = ops.cond_half(bsz, heads)
+        # Samples vs prompts: diffusers repeats every prompt num_images_per_prompt times (prompt-major), and the
+        # reference's keys then enumerate images x heads of its single prompt (the "head" index of a key runs over
+        # the whole kept axis, trace.py:240, 293-294). The slab is therefore [prompts][images * heads]; the kernel
+        # sees the same memory as [samples][heads].
+        n_real = len(self.last_prompts) if self.last_prompts else (n_samples if self.batch_prompts else 1)
+        if n_real > 1 and not self.batch_prompts:
+            raise ValueError('Only single prompt generation is supported for heat map computation.')
+        if n_samples % n_real != 0:
+            raise RuntimeError(f'layer {layer_idx}: {n_samples} conditional samples for {n_real} prompts')
+        images = n_samples // n_real
+        slab = self.all_heat_maps.slab_for(layer_idx, factor, n_real, images * n_heads, side, side, q.device, head0)
+        self._epoch_seen = self.all_heat_maps.epoch        # (this call may have bumped it; the other layers' slabs stand)
+        desc = ops.make_layer_desc(q, k, slab.acc.view(n_samples, n_heads, slab.acc.shape[2], hw), heads, scale)
+        if self.launch == 'step':
+            if pos >= len(self._slots):                    # grow the step array (SDXL: 70 layers)
+                grown = _native.PackedLayers([_native.DaamLayer()] * (2 * len(self._slots)))
+                for i in range(pos):
+                    grown.array[i] = self._packed.array[i]
+                self._packed = grown
+                self._slots = [grown.array[i] for i in range(len(grown.array))]
+                self._layer_state.clear()                  # cached slot proxies point into the old array
+            self._packed.array[pos] = desc
+            slot, own = self._slots[pos], None
+        else:
+            own = _native.PackedLayers([desc])             # 'layer' mode: every layer launches its own 1-element array
+            slot = own.array[0]
+        # the fast path is only valid for contiguous projections (strides implied by the shape)
+        shape_key = q.shape if (q.is_contiguous() and k.is_contiguous()) else None
+        state = (shape_key, q.dtype, pos, slot, slab, desc.q - q.data_ptr(), desc.k - k.data_ptr(), q.get_device(), own)
+        self._layer_state[layer_idx] = state
+        self._device = q.device
+        return state
+
+    def _launch_now(self, own, device):
+        """``launch='layer'``: the layer's kernel right away on the current stream (the producer of Q/K may be the
+        immediately preceding kernel there, so no EARLY_LOADS)."""
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        stream = torch.cuda.current_stream(index).cuda_stream
+        if index == torch.cuda.current_device():
+            _native.accumulate(own, stream, self.kernel_flags)
+        else:
+            with torch.cuda.device(index):
+                _native.accumulate(own, stream, self.kernel_flags)
 
     def _accumulate_probs(self, layer_idx: int, factor: int, probs: torch.Tensor, bsz: int, heads: int):
         """Heat maps from materialised probabilities (save_heads / load_heads compatibility path)."""
         hw = probs.shape[1]
         side = int(math.sqrt(hw))
-        _, n_prompts, head0, n_heads = ops.cond_half(bsz, heads)
-        if n_prompts > 1 and not self.batch_prompts:
+        _, n_samples, head0, n_heads = ops.cond_half(bsz, heads)
+        n_real = len(self.last_prompts) if self.last_prompts else (n_samples if self.batch_prompts else 1)
+        if n_real > 1 and not self.batch_prompts:
             raise ValueError('Only single prompt generation is supported for heat map computation.')
-        slab = self.all_heat_maps.slab_for(layer_idx, factor, n_prompts, n_heads, side, side, probs.device, head0)
+        if n_samples % n_real != 0:
+            raise RuntimeError(f'layer {layer_idx}: {n_samples} conditional samples for {n_real} prompts')
+        slab = self.all_heat_maps.slab_for(layer_idx, factor, n_real, (n_samples // n_real) * n_heads, side, side,
+                                           probs.device, head0)
         self.synchronize()
         ops.accumulate_probs(probs, slab.acc)
 
     def flush(self):
-        """Issue the queued layer calls as one persistent launch on the side stream."""
-        pending = self._pending
-        if not pending:
+        """Issue the queued layer calls as one persistent launch (per pack of 32 layers) on the side stream."""
+        n = self._n_pending
+        if n == 0:
             return
-        device = pending[0][2].device
-        n = len(pending)
+        device = self._device
+        index = device.index if device.index is not None else torch.cuda.current_device()
         packed = self._packed
-        if packed is None or len(packed.array) < n:
-            packed = self._packed = _native.PackedLayers([_native.DaamLayer()] * max(n, 64))
-        for i, item in enumerate(pending):            # struct copies into the reusable host array
-            packed.array[i] = item[1]
         packed.n = n
-        if torch.cuda.is_current_stream_capturing():
-            # CUDA-graph capture of the UNet step: the launch becomes a node of the captured stream itself
-            # (its predecessor on that stream is the tail of the UNet forward, never a producer of the queued Q/K)
-            for item in pending:
-                item[4].captured = True
-            ops.accumulate(packed, device, flags=self.kernel_flags | _native.ACC_EARLY_LOADS)
-        else:
-            side = self._side_stream(device)
-            side.wait_stream(torch.cuda.current_stream(device))   # Q/K were produced on the current stream
-            # the side stream carries nothing but these launches: the projections are complete (event above) before the
-            # previous launch could have started, so only the accumulator updates need to wait for it (EARLY_LOADS)
-            ops.accumulate(packed, device, stream=side, flags=self.kernel_flags | _native.ACC_EARLY_LOADS)
-            # Keep the projections alive until the kernel has run: park the references behind an event instead of
-            # 2 x n_layers record_stream calls; batches whose event has fired are dropped here, one step later.
-            done = torch.cuda.Event()
-            done.record(side)
-            self._inflight = [b for b in self._inflight if not b[0].query()]
-            self._inflight.append((done, [(item[2], item[3]) for item in pending]))
-            self._dirty = True
-        self._pending = []
-        self._pending_layers.clear()
+        flags = self.kernel_flags | _native.ACC_EARLY_LOADS
+        current = torch.cuda.current_stream(index).cuda_stream
+        previous = torch.cuda.current_device()
+        switch = index != previous
+        if switch:
+            torch.cuda.set_device(index)
+        try:
+            if torch.cuda.is_current_stream_capturing():
+                # CUDA-graph capture of the UNet step: the launch becomes a node of the captured stream itself (its
+                # predecessor there is the tail of the UNet forward, never a producer of the queued Q/K: EARLY_LOADS holds)
+                step = self._step_id
+                for layer_idx, st in self._layer_state.items():
+                    if self._queued.get(layer_idx) == step:
+                        st[4].captured = True
+                _native.accumulate(packed, current, flags)
+            else:
+                side = self._side_stream(device)
+                if self._launcher is None:
+                    self._launcher = _native.SideLauncher()
+                if self._parked and self._launcher.idle():     # the previous launches have run: drop their projections
+                    self._parked = []
+                # One foreign call: event on the current stream (Q/K were produced there) -> the side stream waits ->
+                # launch -> `done` event. The side stream carries nothing but these launches and the projections are
+                # complete before the previous one could have started, so only the accumulator updates need to wait
+                # for it (EARLY_LOADS).
+                self._launcher.launch(packed, flags, current, side.cuda_stream)
+                self._parked.append(self._refs)                # alive until a later idle() / join says the kernel has run
+                self._dirty = True
+        finally:
+            if switch:
+                torch.cuda.set_device(previous)
+        self._refs = []
+        self._n_pending = 0
+        self._step_id += 1
 
     def synchronize(self):
         """Make every accumulate issued so far visible to work enqueued on the current stream afterwards."""
         self.flush()
         if self._dirty and self._stream is not None:
-            torch.cuda.current_stream(self._stream.device).wait_stream(self._stream)
+            self._launcher.join(torch.cuda.current_stream(self._stream.device).cuda_stream)
             self._dirty = False
             # parked projections: their memory may only be reused by the current stream after the side stream is done
             # with them, which the wait above now guarantees for everything issued so far
-            self._inflight = []
+            self._parked = []
 
     def _zero_slabs(self, slabs: List[LayerSlab]):
         if not slabs:
@@ -341,6 +409,8 @@ class PipelineHooker(ObjectHooker):
             if len(prompts) > 1 and not tr.batch_prompts:
                 raise ValueError('Only single prompt generation is supported for heat map computation.')
         hk_self.heat_maps.clear()
+        if len(prompts) != len(tr.last_prompts):    # slabs are laid out [prompts][images * heads]: re-derive them
+            tr._layer_state.clear()
         tr.last_prompt = prompts[0]
         tr.last_prompts = prompts
         return hk_self.monkey_super('check_inputs', prompt, *args, **kwargs)
@@ -364,6 +434,7 @@ class UNetCrossAttentionHooker(ObjectHooker):
         self.load_heads = load_heads
         self.save_heads = save_heads
         self.trace = parent_trace
+        self._geom = None
         self.data_dir = Path(data_dir) if data_dir is not None else cache_dir() / 'heads'
         if load_heads or save_heads:
             self.data_dir.mkdir(parents=True, exist_ok=True)
@@ -412,10 +483,14 @@ class UNetCrossAttentionHooker(ObjectHooker):
 
         heads = attn.heads
         tokens = key.shape[1]
-        factor = int(math.sqrt(self.latent_hw // n))
-        self.trace._gen_idx += 1
-        if tokens == self.context_size and factor != 8:      # skip if too large (trace.py:289)
-            self.trace._enqueue(self.layer_idx, factor, query, key, heads, attn.scale)
+        geom = self._geom                                    # (n, tokens) -> factor and the trace / skip decision
+        if geom is None or geom[0] != n or geom[1] != tokens:
+            factor = int(math.sqrt(self.latent_hw // n))
+            geom = self._geom = (n, tokens, factor, tokens == self.context_size and factor != 8)   # trace.py:285-289
+        tr = self.trace
+        tr._gen_idx += 1
+        if geom[3]:                                          # skip if too large (trace.py:289)
+            tr._enqueue(self.layer_idx, geom[2], query, key, heads, attn.scale)
 
         d = query.shape[-1] // heads
         q4 = query.view(bsz, n, heads, d).transpose(1, 2)

@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 #define DAAM_ABI_VERSION 3          /* 2: + daam_attention_probs, daam_accumulate_probs, daam_finalize_per_key
-                                       3: + DAAM_ACC_EARLY_LOADS, daam_expand_words */
+                                       3: + DAAM_ACC_EARLY_LOADS, daam_expand_words, daam_side_launcher_* */
 #define DAAM_TOKENS 77          /* context length the reference traces (daam/trace.py:194, guard at :289) */
 #define DAAM_MAX_HEAD_DIM 256   /* any multiple of 8 up to here (SD-1.x deepest level: 1280 channels / 8 heads = 160) */
 
@@ -50,6 +50,7 @@ enum daam_dtype { DAAM_F32 = 0, DAAM_F16 = 1, DAAM_BF16 = 2 };
 #define DAAM_ACC_RMW_RED    0x20u /* red.global.add.f32 (SIMT) / bulk-async reduce-add from shared memory (MMA) */
 #define DAAM_ACC_NO_PDL     0x100u /* launch without programmatic dependent launch (measurement / debugging) */
 #define DAAM_ACC_RED_SEGMENTS 0x400u /* tcgen05 kernel, RED mode: 7 bulk-tensor reduce-adds of 11 token rows per tile */
+#define DAAM_ACC_RED_REGS   0x1000u /* tcgen05 kernel, RED mode: red.global.add.f32 from registers, no staging */
 #define DAAM_ACC_RED_ROWS   0x800u /* tcgen05 kernel, RED mode: 77 one-row bulk reduce-adds per tile (one per thread) */
 #define DAAM_ACC_EARLY_LOADS 0x200u /* The caller vouches that q and k of every layer were complete BEFORE the previous
                                      kernel on `stream` started (they were produced on another stream and joined through
@@ -90,6 +91,25 @@ typedef struct daam_layer {
 /* Enqueue the fused softmax(QK^T) -> unravel -> accumulate kernel over `n_layers` layer calls (any number; the
  * library packs them into as few persistent launches as possible). `layers` is host memory, read before returning. */
 int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint32_t flags, void* stream);
+
+/*
+ * The tracer's step launch (daam_b200/trace.py flush): the reference's hook does its heat-map work inline on the
+ * pipeline's stream (daam/trace.py:276-294); here one launch per denoising step runs on a SIDE stream so that it overlaps
+ * the next step's UNet forward. This helper does the stream plumbing of that launch in one foreign call:
+ *   launch: record an event on `producer_stream` (where to_q / to_k ran), make `side_stream` wait for it,
+ *           daam_accumulate(layers, n_layers, flags, side_stream), record the launcher's `done` event on side_stream;
+ *   join:   make `stream` wait for the last launch (before anything reads the accumulators or frees the projections);
+ *   idle:   1 if the last launch has completed (the caller may then drop its references to that step's q / k), 0 if
+ *           it is still running, negative on error.
+ * The launcher owns two CUDA events and nothing else. Not thread-safe; one launcher per tracer.
+ */
+typedef struct daam_side_launcher daam_side_launcher;
+int daam_side_launcher_create(daam_side_launcher** out);
+void daam_side_launcher_destroy(daam_side_launcher* launcher);
+int daam_side_launcher_launch(daam_side_launcher* launcher, const daam_layer* layers, int32_t n_layers, uint32_t flags,
+                              void* producer_stream, void* side_stream);
+int daam_side_launcher_join(daam_side_launcher* launcher, void* stream);
+int daam_side_launcher_idle(daam_side_launcher* launcher);
 
 /*
  * Compatibility path of the reference's save_heads: materialise what Attention.get_attention_scores returns

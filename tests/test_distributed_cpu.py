@@ -36,7 +36,7 @@ def _worker(rank, world, port, n_total, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n_total', [4, 5])
+@pytest.mark.parametrize('n_total', [4, 5, 1])     # 1 < world: rank 1 owns no prompt and still joins the collective
 def test_gather_heat_maps_world2(tmp_path, n_total):
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))

@@ -288,3 +288,36 @@ def test_sd1x_style_pipeline(dtype, tol):
         ref = O.port_global_heat_map(store, 4096, n_tok)
         assert rel_err(tc.compute_global_heat_map().heat_maps, ref) < tol
     assert {c[2].shape[-1] // c[4] for c in rec.calls} == {40, 80}
+
+
+def test_several_images_per_prompt_enumerate_images_x_heads_like_the_reference():
+    """num_images_per_prompt > 1: the CFG batch is [uncond x n, cond x n] for ONE prompt and the reference's keys run over
+    images x heads (`map_[map_.size(0) // 2:]` keeps n * H rows, trace.py:240, 293-294). Same here: one prompt, n * H keys
+    per layer, each equal to the oracle's map for that (image, head)."""
+    from tests.util import assert_elementwise
+    pipe = make_pipeline(TINY_SPEC, dtype=torch.float16, device=DEV, seed=6)
+    spec = pipe.unet.spec
+    g = torch.Generator().manual_seed(3)
+    n = 2
+    lat = torch.randn(2 * n, spec.in_channels, 64, 64, generator=g).half().to(DEV)
+    emb = torch.randn(2 * n, 77, spec.cross_attention_dim, generator=g).half().to(DEV)
+    calls = []
+    with torch.no_grad(), trace(pipe) as tc:
+        inner = tc._enqueue
+
+        def enqueue(layer_idx, factor, q, k, heads, scale):
+            calls.append((layer_idx, factor, q.detach().float().cpu(), k.detach().float().cpu(), heads, scale))
+            return inner(layer_idx, factor, q, k, heads, scale)
+
+        tc._enqueue = enqueue
+        tc.last_prompts, tc.last_prompt = ['a cat'], 'a cat'
+        pipe.unet(lat, torch.full((1,), 500.0, device=DEV), emb)
+        got = dict(tc.all_heat_maps)
+        for layer_idx, factor, q, k, heads, scale in calls:
+            ref = O.port_layer_step(q, k, heads, scale)            # [n * H, 77, h, w]: the reference's kept half
+            assert ref.shape[0] == n * heads
+            for key_head in range(n * heads):
+                assert_elementwise(got[(factor, layer_idx, key_head)], ref[key_head], 1e-4, 1e-5, f'{layer_idx}/{key_head}')
+        assert len(got) == n * 25
+        out = tc.compute_global_heat_map().heat_maps                 # mean over images x heads x layers, one prompt
+        assert out.shape == (4, 64, 64)
