@@ -507,7 +507,7 @@ def run_reference(args):
         pipe(prompt, num_inference_steps=steps)
         sync()
         t_steps = time.time() - t0
-        maps = ot.compute_global_heat_map().heat_maps.cpu()
+        maps = ot.compute_global_heat_map().cpu()
         dt = time.time() - t0
     assert torch.isfinite(maps.float()).all()
     ms = dt / steps * 1e3

@@ -17,7 +17,6 @@ DAAM_F32, DAAM_F16, DAAM_BF16 = 0, 1, 2
 ACC_AUTO, ACC_FORCE_SIMT, ACC_FORCE_MMA = 0, 1, 2
 ACC_RMW_AUTO, ACC_RMW_LDST, ACC_RMW_RED = 0x00, 0x10, 0x20
 ACC_NO_PDL = 0x100
-ACC_RED_SEGMENTS, ACC_RED_ROWS, ACC_RED_REGS = 0x400, 0x800, 0x1000
 ACC_EARLY_LOADS = 0x200   # see include/daam_b200.h: only valid when q/k were complete before the previous kernel started
 ABI_VERSION = 3
 E_INVALID, E_UNSUPPORTED, E_CUDA = -1, -2, -3

@@ -18,12 +18,12 @@
 //
 // fp32 projections (the reference's default dtype for SD-1.x/2.x, daam/run/generate.py:205) take the same kernel in
 // "split" form. Tensor cores have no fp32 operand type and a plain kind::tf32 product would drop 13 mantissa bits, so
-// every value is used as two tf32 terms, x = hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi) (22 significand
-// bits, unbiased), and q.k = q_lo.k_hi + q_hi.k_lo + q_hi.k_hi (the dropped terms are <= 2^-22 relative): the fp32
-// Q/K tiles arrive by TMA exactly like the 16-bit ones (two 128-byte-wide swizzled sub-tiles per 64 dims), four
-// converter warps rewrite the landed tile in place to `hi` and emit `lo` into a second buffer (a shared-memory ->
-// shared-memory elementwise pass, swizzle-agnostic), and the MMA thread issues 3 x 8 tcgen05.mma kind::tf32 (K = 8)
-// per tile. One CTA per SM (two 52 KB raw stages + one lo buffer + the staged probabilities).
+// every value is used as two tf32 terms, x = hi + lo with hi = trunc_tf32(x) -- what the tensor core reads from the raw
+// fp32 container -- and lo = rna_tf32(x - hi) (22 significand bits), and q.k = q_lo.k_hi + q_hi.k_lo + q_hi.k_hi (the
+// dropped terms are ~2^-22 relative): the fp32 Q/K tiles arrive by TMA exactly like the 16-bit ones (two 128-byte-wide
+// swizzled sub-tiles per 64 dims) and ARE the hi operands; eight converter warps emit `lo` into a second buffer (a
+// shared-memory -> shared-memory elementwise pass, swizzle-agnostic), and the MMA thread issues 3 x 8 tcgen05.mma
+// kind::tf32 (K = 8) per tile. One CTA per SM (two 52 KB raw stages + one lo buffer + the staged probabilities).
 //
 // head_dim other than 64 (SD-1.x: 40 / 80 / 160): the contraction runs in 64-wide K chunks, one chunk per smem stage,
 // accumulated into the same TMEM accumulator; the last chunk is zero-filled beyond head_dim (by the TMA unit, or by the
@@ -31,7 +31,6 @@
 //
 // Replaces daam/trace.py:276 (get_attention_scores), :219-244 (_unravel_attn) and :293-294 (update loop).
 #include <cuda.h>
-#include <stdlib.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -55,7 +54,7 @@ constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kPBytes + kBarBytes;
 // split (fp32) form: a raw stage holds the fp32 tiles as [Q sub0][Q sub1][K sub0][K sub1] (sub-tile = 32 floats = one
 // 128-byte swizzle span per row); one more buffer of the same shape holds the lo terms; warps 6-9 convert
 constexpr int kSplitStageBytes = 2 * kStageBytes;     // 53248 = 52 x 1024
-constexpr int kSplitThreads = 448;                   // launch bound; 192 + 32 x converter warps (4 or 8) at run time
+constexpr int kSplitThreads = 448;                   // 6 warps as in the 16-bit form + 8 converter warps
 constexpr int kSplitSmemBytes = 1024 + (kStages + 1) * kSplitStageBytes + kPBytes + kBarBytes;
 static_assert(kSplitSmemBytes <= 232448, "split form exceeds the 227 KB shared-memory limit");
 
@@ -64,10 +63,7 @@ struct MmaParams {
   CUtensorMap qmap[kMaxLayersPerLaunch];
   CUtensorMap kmap[kMaxLayersPerLaunch];
   CUtensorMap amap[kMaxLayersPerLaunch];
-  CUtensorMap amap_seg[kMaxLayersPerLaunch];       // same tensor, box = [11 tokens x 128 pixels] (segmented reduce)
 };
-constexpr int kSegTokens = 11, kSegs = kTokens / kSegTokens;        // 77 = 7 x 11
-static_assert(kSegs * kSegTokens == kTokens, "token segments must tile 77");
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,18 +112,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
                "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
-__device__ __forceinline__ void bulk_reduce_add_1d(float* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
-               : "memory");
-}
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -208,24 +197,30 @@ __device__ __forceinline__ float rna_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-// Converter warps (split form): a landed fp32 region [begin, end) of a raw stage (16-byte units, any swizzle -- the pass
-// is elementwise) is rewritten in place to hi = rna_tf32(x) and lo = rna_tf32(x - hi) goes to the same offsets of the lo
-// buffer. x - hi is exact in fp32 (|x - hi| <= half a tf32 ulp of x), so hi + lo carries 22 significand bits of x.
-__device__ __forceinline__ void split_region(uint8_t* raw, uint8_t* lo, int begin, int end, int ctid, int n_conv,
-                                             bool write_hi) {
-#pragma unroll 4
-  for (int off = begin + ctid * 16; off < end; off += n_conv * 16) {
-    float4 x = *reinterpret_cast<const float4*>(raw + off);
-    float4 h, l;
-    if (write_hi) {
-      h.x = rna_tf32(x.x); h.y = rna_tf32(x.y); h.z = rna_tf32(x.z); h.w = rna_tf32(x.w);
-      *reinterpret_cast<float4*>(raw + off) = h;
-    } else {   // EXPERIMENT: the tensor core truncates the container itself; lo = x - trunc(x)
-      h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-      h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-    }
-    l.x = rna_tf32(x.x - h.x); l.y = rna_tf32(x.y - h.y); l.z = rna_tf32(x.z - h.z); l.w = rna_tf32(x.w - h.w);
-    *reinterpret_cast<float4*>(lo + off) = l;
+// hi term of the split as the tensor core sees it: kind::tf32 reads the upper 19 bits of the 32-bit container and
+// ignores the low 13 mantissa bits, i.e. hi = trunc_tf32(x). (Pinned by tests/test_parity_elementwise_gpu.py: were the
+// hardware to round instead, hi + lo would be off by a tf32 ulp and every fp32 parity test would fail at 1e-3.)
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// Converter warps (split form): for a landed fp32 region [begin, end) of a raw stage (16-byte units, any swizzle -- the
+// pass is elementwise) write lo = rna_tf32(x - trunc_tf32(x)) to the same offsets of the lo buffer. The raw tile itself is
+// the hi operand (see trunc_tf32): it is not rewritten. x - trunc_tf32(x) is exact in fp32 (13 significant bits), so
+// hi + lo carries 22 significand bits of x. Four units per thread are loaded before the first is processed.
+__device__ __forceinline__ void split_region(const uint8_t* raw, uint8_t* lo, int begin, int end, int ctid, int n_conv) {
+  const int stride = n_conv * 16;
+  for (int off = begin + ctid * 16; off < end; off += 4 * stride) {
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (off + u * stride < end) x[u] = *reinterpret_cast<const float4*>(raw + off + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (off + u * stride < end) {
+        float4 l;
+        l.x = rna_tf32(x[u].x - trunc_tf32(x[u].x)); l.y = rna_tf32(x[u].y - trunc_tf32(x[u].y));
+        l.z = rna_tf32(x[u].z - trunc_tf32(x[u].z)); l.w = rna_tf32(x[u].w - trunc_tf32(x[u].w));
+        *reinterpret_cast<float4*>(lo + off + u * stride) = l;
+      }
   }
 }
 
@@ -266,7 +261,7 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
       mbar_init(tfull0 + 8 * a, 1);
       mbar_init(tempty0 + 8 * a, 4);       // one arrival per epilogue warp
     }
-    mbar_init(lofull, kSplit ? (blockDim.x - 192) / 32 : 1);   // one arrival per converter warp
+    mbar_init(lofull, (kSplitThreads - 192) / 32);  // one arrival per converter warp
     mbar_init(loempty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -301,8 +296,7 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
 
   if (kSplit && warp >= 6) {
     // ===== converter warps (fp32 projections): landed fp32 tile -> hi (in place) + lo (second buffer) =====
-    const int ctid = threadIdx.x - 192, n_conv = blockDim.x - 192;
-    const bool write_hi = !(P.pad_ & 1);
+    const int ctid = threadIdx.x - 192, n_conv = kSplitThreads - 192;
     uint8_t* lo = gen + kStages * kStageBytesT;
     int li = 0, j = 0;
     for (int i = 0; i < count; ++i) {
@@ -315,8 +309,8 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
         mbar_wait(full0 + 8 * s, (uint32_t)(j / kStages) & 1u);         // TMA has landed the raw tiles
         mbar_wait(loempty, ((uint32_t)j & 1u) ^ 1u);                   // the MMAs of the previous chunk have read lo
         uint8_t* stage = gen + s * kStageBytesT;
-        split_region(stage, lo, 0, subs * kQBytes, ctid, n_conv, write_hi);
-        split_region(stage, lo, 2 * kQBytes, 2 * kQBytes + subs * kKBytes, ctid, n_conv, write_hi);
+        split_region(stage, lo, 0, subs * kQBytes, ctid, n_conv);
+        split_region(stage, lo, 2 * kQBytes, 2 * kQBytes + subs * kKBytes, ctid, n_conv);
         fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core's reads
         __syncwarp();
         if (lane == 0) mbar_arrive(lofull);
@@ -449,51 +443,6 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
           bulk_commit();
         }
         issued = true;
-      } else if (P.rmw_mode == 2) {
-        // segmented: 7 reduce-adds of 11 token rows each, one bulk group per segment, so that segment g of this tile
-        // only waits for segment g of the previous tile (up to 7 reduces in flight per CTA instead of 1)
-#pragma unroll
-        for (int g = 0; g < kSegs; ++g) {
-          if (tid == 0 && issued) bulk_wait_read<kSegs - 1>();
-          epi_barrier();
-#pragma unroll
-          for (int j = g * kSegTokens; j < (g + 1) * kSegTokens; ++j) sP[j * kTilePixels + tid] = v[j] * inv;
-          fence_proxy_async();
-          epi_barrier();
-          if (tid == 0) {
-            tma_reduce_add_2d(&MP.amap_seg[t.li], sP_u32 + g * kSegTokens * kTilePixels * 4, t.pixel0,
-                              (t.prompt * L.heads + t.head) * kTokens + g * kSegTokens);
-            bulk_commit();
-          }
-        }
-        issued = true;
-      } else if (P.rmw_mode == 3) {
-        // row reduces: thread j < 77 owns token row j of the staged tile and sends it as its own 1-D bulk reduce-add
-        // (77 independent bulk groups in flight per CTA; bytes clip partial tiles)
-        if (tid < kTokens && issued) bulk_wait_read0();
-        epi_barrier();
-#pragma unroll
-        for (int j = 0; j < kTokens; ++j) sP[j * kTilePixels + tid] = v[j] * inv;
-        fence_proxy_async();
-        epi_barrier();
-        if (tid < kTokens) {
-          const int live = min(kTilePixels, L.hw - t.pixel0);
-          float* dst = L.acc + ((long long)(t.prompt * L.heads + t.head) * kTokens + tid) * L.hw + t.pixel0;
-          bulk_reduce_add_1d(dst, sP_u32 + tid * kTilePixels * 4, (uint32_t)live * 4u);
-          bulk_commit();
-        }
-        issued = true;
-      } else if (P.rmw_mode == 4) {
-        // register reds: red.global.add.f32 straight from the softmax registers, one 128-byte coalesced reduction per
-        // warp and token; fire-and-forget (no staging buffer, nothing to wait for before the next tile)
-        const int pixel = t.pixel0 + tid;
-        if (pixel < L.hw) {
-          const long long hw = L.hw;
-          float* acc = L.acc + ((long long)(t.prompt * L.heads + t.head) * kTokens) * hw + pixel;
-#pragma unroll
-          for (int j = 0; j < kTokens; ++j)
-            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(acc + j * hw), "f"(v[j] * inv) : "memory");
-        }
       } else {
         const int pixel = t.pixel0 + tid;
         if (pixel < L.hw) {
@@ -512,7 +461,7 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
       }
     }
     // shared memory must outlive the reduce's reads; its global writes complete with the grid (same rule as a TMA store)
-    if (issued && (tid == 0 || (P.rmw_mode == 3 && tid < kTokens))) bulk_wait_read0();
+    if (tid == 0 && issued) bulk_wait_read0();
   }
 
   tc_fence_before();
@@ -597,9 +546,9 @@ int make_qk_map(const void* ptr, int dtype, int head_dim, int heads, int rows, i
   return DAAM_OK;
 }
 
-// accumulator as a 2-D fp32 tensor {hw, prompts*heads*77}; box = [box_tokens x 128 pixels], no swizzle.
-int make_acc_map(float* acc, int hw, int rows, int box_tokens, CUtensorMap* out) {
-  MapKey key{acc, 0, 0, 0, hw, rows, box_tokens, 1};
+// accumulator as a 2-D fp32 tensor {hw, prompts*heads*77}; box = [77 tokens x 128 pixels], no swizzle.
+int make_acc_map(float* acc, int hw, int rows, CUtensorMap* out) {
+  MapKey key{acc, 0, 0, 0, hw, rows, 0, 1};
   {
     std::lock_guard<std::mutex> lock(g_map_mu);
     auto it = map_cache().find(key);
@@ -609,7 +558,7 @@ int make_acc_map(float* acc, int hw, int rows, int box_tokens, CUtensorMap* out)
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DAAM_E_CUDA; }
   const cuuint64_t dims[2] = {(cuuint64_t)hw, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)hw * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)kTilePixels, (cuuint32_t)box_tokens};
+  const cuuint32_t box[2] = {(cuuint32_t)kTilePixels, (cuuint32_t)kTokens};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, acc, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -651,8 +600,7 @@ int prepare_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, void* o
     if ((L.dtype == DAAM_F32) != split) { set_error("mixed fp32 / 16-bit layers in one tcgen05 pack"); return DAAM_E_INVALID; }
     if (int rc = make_qk_map(L.q, L.dtype, L.head_dim, L.heads, L.hw, L.n_prompts, L.qs_head, L.qs_pixel, L.qs_prompt, kTilePixels, &mp.qmap[i])) return rc;
     if (int rc = make_qk_map(L.k, L.dtype, L.head_dim, L.heads, kTokens, L.n_prompts, L.ks_head, L.ks_token, L.ks_prompt, kTokensPad, &mp.kmap[i])) return rc;
-    if (int rc = make_acc_map(L.acc, L.hw, L.n_prompts * L.heads * kTokens, kTokens, &mp.amap[i])) return rc;
-    if (int rc = make_acc_map(L.acc, L.hw, L.n_prompts * L.heads * kTokens, kSegTokens, &mp.amap_seg[i])) return rc;
+    if (int rc = make_acc_map(L.acc, L.hw, L.n_prompts * L.heads * kTokens, &mp.amap[i])) return rc;
     chunked = chunked || L.head_dim > 64;
   }
   cudaError_t attr_err = cudaSuccess;
@@ -661,23 +609,16 @@ int prepare_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, void* o
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
       if (e != cudaSuccess) attr_err = e;
     };
-    set((const void*)accumulate_mma_kernel<false, false>, 120 * 1024);
-    set((const void*)accumulate_mma_kernel<false, true>, 120 * 1024);
+    set((const void*)accumulate_mma_kernel<false, false>, kSmemBytes);
+    set((const void*)accumulate_mma_kernel<false, true>, kSmemBytes);
     set((const void*)accumulate_mma_kernel<true, false>, kSplitSmemBytes);
     set((const void*)accumulate_mma_kernel<true, true>, kSplitSmemBytes);
   });
   DAAM_CUDA_TRY(attr_err);
-  // EXPERIMENT knobs (environment, read per prepare): converter warps, hi rewrite, one 16-bit CTA per SM
-  const char* e_conv = getenv("DAAM_SPLIT_CONV_WARPS");
-  const char* e_nohi = getenv("DAAM_SPLIT_NO_HI");
-  const char* e_one = getenv("DAAM_MMA_ONE_CTA");
-  const int conv_warps = e_conv && e_conv[0] == '8' ? 8 : 4;
-  if (e_nohi && e_nohi[0] == '1') mp.base.pad_ |= 1;
-  const bool one_cta = !split && e_one && e_one[0] == '1';
-  pm.grid = dev.sm_count * (split || one_cta ? 1 : 2);
+  pm.grid = dev.sm_count * (split ? 1 : 2);
   if (pm.grid > p.total_tiles) pm.grid = p.total_tiles;
-  pm.block = split ? 192 + 32 * conv_warps : kThreads;
-  pm.smem = split ? kSplitSmemBytes : one_cta ? 120 * 1024 : kSmemBytes;
+  pm.block = split ? kSplitThreads : kThreads;
+  pm.smem = split ? kSplitSmemBytes : kSmemBytes;
   pm.variant = (split ? 1 : 0) | (chunked ? 2 : 0);
   return DAAM_OK;
 }

@@ -114,7 +114,7 @@ int build_plan(const daam_layer* layers, int n_layers, uint32_t flags, const Dev
   LaunchParams packs[3];                 // 0: tcgen05 16-bit, 1: tcgen05 fp32, 2: SIMT
   for (LaunchParams& p : packs) {
     p.n_layers = p.total_tiles = 0;
-    p.rmw_mode = (rmw == DAAM_ACC_RMW_LDST) ? 0 : (flags & DAAM_ACC_RED_REGS) ? 4 : (flags & DAAM_ACC_RED_ROWS) ? 3 : (flags & DAAM_ACC_RED_SEGMENTS) ? 2 : 1;
+    p.rmw_mode = (rmw == DAAM_ACC_RMW_LDST) ? 0 : 1;     // default: reduce-add
     p.pdl = (flags & DAAM_ACC_NO_PDL) ? 0 : 1;
     p.early_loads = (flags & DAAM_ACC_EARLY_LOADS) && p.pdl ? 1 : 0;
     p.pad_ = 0;

@@ -164,6 +164,112 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+template <int F>
+__device__ __forceinline__ void class_pass(const FinalizeParams& P, int side, int nk, int band, int br, float* tile,
+                                           const float* const* keys, float* stage) {
+  const int x = P.x;
+  const int R = br / F;                                // source rows under this band
+  const int VR = R + 4;                                // + 2 halo rows above and below
+  const int region = VR * side;                        // floats of one key's staged rows
+  const int n_src = R * side;                          // source pixels under the band (<= 256, checked by the host)
+  const int kg = 256 / n_src;                          // thread groups that split the keys
+  int kc = kStageFloats / region;                      // keys per chunk, a multiple of kg so every group keeps its stride
+  kc -= kc % kg;
+  const int n_chunks = (nk + kc - 1) / kc;
+  const int row_units = side / 4, key_units = VR * row_units;     // 16-byte units
+  const int sy0 = band * R;
+
+  auto issue = [&](int c) {
+    float* buf = stage + (c & 1) * kStageFloats;
+    const int k0 = c * kc, kn = min(kc, nk - k0);
+    for (int u = threadIdx.x; u < kn * key_units; u += blockDim.x) {
+      const int k = u / key_units, rem = u - k * key_units;
+      const int vr = rem / row_units, c4 = rem - vr * row_units;
+      const int row = min(max(sy0 - 2 + vr, 0), side - 1);          // border rows are replicated, as the taps clamp
+      cp_async16(buf + k * region + vr * side + 4 * c4, keys[k0 + k] + row * side + 4 * c4);
+    }
+    cp_async_commit();
+  };
+
+  const int group = (int)threadIdx.x / n_src;
+  const int s = (int)threadIdx.x - group * n_src;
+  const bool live = group < kg;
+  const int ly = s / side, sx = s - ly * side;
+  int ix[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) ix[j] = min(max(sx - 2 + j, 0), side - 1);
+  PhaseWeights<F> pw;
+  pw.init();
+  float acc[F][F];
+#pragma unroll
+  for (int py = 0; py < F; ++py)
+#pragma unroll
+    for (int px = 0; px < F; ++px) acc[py][px] = 0.f;
+
+  if (n_chunks > 0) issue(0);
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c + 1 < n_chunks) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();                                   // chunk c has landed for every thread
+    if (live) {
+      const float* buf = stage + (c & 1) * kStageFloats + ly * side;
+      const int kn = min(kc, nk - c * kc);
+      for (int k = group; k < kn; k += kg) {
+        const float* src = buf + k * region;
+        float v[5][5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+          for (int j = 0; j < 5; ++j) v[i][j] = src[i * side + ix[j]];
+        add_key<F>(pw, v, acc);
+      }
+    }
+    __syncthreads();                                   // buffer (c & 1) may be overwritten by chunk c + 2
+  }
+  for (int g = 0; g < kg; ++g) {                       // merge the key groups in a fixed order
+    if (live && group == g) {
+      const int oy0 = ly * F, ox0 = sx * F;
+#pragma unroll
+      for (int py = 0; py < F; ++py)
+#pragma unroll
+        for (int px = 0; px < F; ++px) tile[(oy0 + py) * x + ox0 + px] += acc[py][px];
+    }
+    __syncthreads();
+  }
+}
+
+// factor 1: bicubic at scale 1 is the identity, the class contributes clamp(src) -- coalesced float4 reads; when the
+// band has fewer float4s than threads, the spare thread groups take every kg-th key (merged in a fixed order)
+__device__ __forceinline__ void class_pass_identity(const FinalizeParams& P, int nk, int band, int br, float* tile,
+                                                    const float* const* keys) {
+  const int x = P.x;
+  const int n4 = br * x / 4;
+  const int kg = n4 >= 256 ? 1 : 256 / n4;
+  const int passes = (n4 + 255) / 256;
+  for (int pass = 0; pass < passes; ++pass) {
+    const int group = n4 >= 256 ? 0 : (int)threadIdx.x / n4;
+    const int i = n4 >= 256 ? pass * 256 + (int)threadIdx.x : (int)threadIdx.x % n4;
+    const bool live = i < n4 && group < kg;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      const long long off = (long long)band * br * x + 4 * i;
+#pragma unroll 8
+      for (int k = group; k < nk; k += kg) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(keys[k] + off));
+        acc.x += fmaxf(v.x, 0.f); acc.y += fmaxf(v.y, 0.f); acc.z += fmaxf(v.z, 0.f); acc.w += fmaxf(v.w, 0.f);
+      }
+    }
+    for (int g = 0; g < kg; ++g) {
+      if (live && group == g) {
+        float4* dst = reinterpret_cast<float4*>(tile + 4 * i);
+        float4 cur = *dst;
+        cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
+        *dst = cur;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 struct ClassList {
   int n;
   int band_rows;            // 8, or 4 when that is what fills the machine / keeps a band's source pixels within one CTA
@@ -172,29 +278,7 @@ struct ClassList {
   int key_slot[kMaxGroups]; // where group g's first selected key goes in keys[]
 };
 
-// Geometry of one class for a band of `br` output rows (all derived from side and x; a handful of integer ops).
-struct ClassGeom {
-  int side, f, rows, region, n_src, kg, kc, n_keys, key0, n_chunks, row_units;
-  __device__ __forceinline__ ClassGeom(const ClassList& C, int c, int x, int br) {
-    side = C.side[c];
-    f = x / side;
-    const int r = br / f;                              // source rows under the band
-    rows = f == 1 ? r : r + 4;                         // staged rows: + 2 halo rows above and below for the cubic taps
-    region = rows * side;                              // floats of one key's staged rows
-    n_src = f == 1 ? r * side / 4 : r * side;          // work items of the band: float4s (identity) or source pixels
-    kg = 256 / n_src;                                  // thread groups that split the keys (n_src <= 256, host-checked)
-    kc = kStageFloats / region;
-    kc -= kc % kg;                                     // keys per chunk: a multiple of kg, so every group keeps its stride
-    key0 = C.key_begin[c];
-    n_keys = C.key_begin[c + 1] - key0;
-    n_chunks = (n_keys + kc - 1) / kc;
-    row_units = side / 4;                              // 16-byte units per staged row
-  }
-};
-
-// grid: (x / band_rows bands, n_rows); dynamic smem: two chunk buffers + the band tile (band_rows * x floats).
-// The chunks of ALL classes form one double-buffered cp.async stream (the first chunk of the next class is in flight
-// while the last chunk of the current one is being reduced), so only the very first chunk's latency is exposed.
+// grid: (x / band_rows bands, n_rows); dynamic smem: two chunk buffers + the band tile (band_rows * x floats)
 __global__ void __launch_bounds__(256, 2) finalize_fast_kernel(const __grid_constant__ FinalizeParams P,
                                                                const __grid_constant__ ClassList C,
                                                                float* __restrict__ out) {
@@ -213,111 +297,14 @@ __global__ void __launch_bounds__(256, 2) finalize_fast_kernel(const __grid_cons
   }
   for (int i = threadIdx.x; i < br * x; i += blockDim.x) tile[i] = 0.f;
   __syncthreads();
-
-  auto issue = [&](int c, int q, int buf_idx) {
-    const ClassGeom G(C, c, x, br);
-    float* buf = stage + buf_idx * kStageFloats;
-    const int k0 = q * G.kc, kn = min(G.kc, G.n_keys - k0);
-    const int key_units = G.rows * G.row_units;
-    const int sy0 = band * (br / G.f) - (G.f == 1 ? 0 : 2);
-    for (int u = threadIdx.x; u < kn * key_units; u += blockDim.x) {
-      const int k = u / key_units, rem = u - k * key_units;
-      const int vr = rem / G.row_units, c4 = rem - vr * G.row_units;
-      const int row = min(max(sy0 + vr, 0), G.side - 1);            // border rows are replicated, as the taps clamp
-      cp_async16(buf + k * G.region + vr * G.side + 4 * c4, keys[G.key0 + k0 + k] + row * G.side + 4 * c4);
-    }
-    cp_async_commit();
-  };
-
-  float acc[16];
-  int c = 0, q = 0, it = 0;
-  issue(0, 0, 0);                                      // class 0 is never empty (host)
-  while (c < C.n) {
-    const ClassGeom G(C, c, x, br);
-    int nc = c, nq = q + 1;                            // the chunk after this one, possibly in the next class
-    if (nq == G.n_chunks) { nc = c + 1; nq = 0; }
-    if (nc < C.n) { issue(nc, nq, (it + 1) & 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-    __syncthreads();                                   // chunk (c, q) has landed for every thread
-
-    const int group = (int)threadIdx.x / G.n_src;
-    const int s = (int)threadIdx.x - group * G.n_src;
-    const bool live = group < G.kg;
-    if (q == 0) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-    }
-    const float* buf = stage + (it & 1) * kStageFloats;
-    const int kn = min(G.kc, G.n_keys - q * G.kc);
-    if (live) {
-      if (G.f == 1) {
-        for (int k = group; k < kn; k += G.kg) {
-          const float4 v = *reinterpret_cast<const float4*>(buf + k * G.region + 4 * s);
-          acc[0] += fmaxf(v.x, 0.f); acc[1] += fmaxf(v.y, 0.f); acc[2] += fmaxf(v.z, 0.f); acc[3] += fmaxf(v.w, 0.f);
-        }
-      } else {
-        const int ly = s / G.side, sx = s - ly * G.side;
-        int ix[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) ix[j] = min(max(sx - 2 + j, 0), G.side - 1);
-        const float* base = buf + ly * G.side;
-        if (G.f == 2) {
-          PhaseWeights<2> pw;
-          pw.init();
-          float (&a2)[2][2] = *reinterpret_cast<float (*)[2][2]>(acc);
-          for (int k = group; k < kn; k += G.kg) {
-            float v[5][5];
-#pragma unroll
-            for (int i = 0; i < 5; ++i)
-#pragma unroll
-              for (int j = 0; j < 5; ++j) v[i][j] = base[k * G.region + i * G.side + ix[j]];
-            add_key<2>(pw, v, a2);
-          }
-        } else {
-          PhaseWeights<4> pw;
-          pw.init();
-          float (&a4)[4][4] = *reinterpret_cast<float (*)[4][4]>(acc);
-          for (int k = group; k < kn; k += G.kg) {
-            float v[5][5];
-#pragma unroll
-            for (int i = 0; i < 5; ++i)
-#pragma unroll
-              for (int j = 0; j < 5; ++j) v[i][j] = base[k * G.region + i * G.side + ix[j]];
-            add_key<4>(pw, v, a4);
-          }
-        }
-      }
-    }
-    __syncthreads();                                   // buffer (it & 1) may be overwritten by the chunk after next
-    if (q + 1 == G.n_chunks) {
-      // end of the class: merge the key groups into the band tile in a fixed order (deterministic sums)
-      for (int g = 0; g < G.kg; ++g) {
-        if (live && group == g) {
-          if (G.f == 1) {
-            float4* dst = reinterpret_cast<float4*>(tile + 4 * s);
-            float4 cur = *dst;
-            cur.x += acc[0]; cur.y += acc[1]; cur.z += acc[2]; cur.w += acc[3];
-            *dst = cur;
-          } else {
-            const int ly = s / G.side, sx = s - ly * G.side;
-            const int oy0 = ly * G.f, ox0 = sx * G.f;
-            if (G.f == 2) {
-#pragma unroll
-              for (int py = 0; py < 2; ++py)
-#pragma unroll
-                for (int px = 0; px < 2; ++px) tile[(oy0 + py) * x + ox0 + px] += acc[py * 2 + px];
-            } else {
-#pragma unroll
-              for (int py = 0; py < 4; ++py)
-#pragma unroll
-                for (int px = 0; px < 4; ++px) tile[(oy0 + py) * x + ox0 + px] += acc[py * 4 + px];
-            }
-          }
-        }
-        __syncthreads();
-      }
-    }
-    c = nc; q = nq; ++it;
+  for (int c = 0; c < C.n; ++c) {
+    const int side = C.side[c], f = x / side, nk = C.key_begin[c + 1] - C.key_begin[c];
+    const float* const* ck = keys + C.key_begin[c];
+    if (f == 1) class_pass_identity(P, nk, band, br, tile, ck);
+    else if (f == 2) class_pass<2>(P, side, nk, band, br, tile, ck, stage);
+    else class_pass<4>(P, side, nk, band, br, tile, ck, stage);
   }
+  __syncthreads();
   float* dst = out + (long long)t * x * x + (long long)band * br * x;
   for (int i = threadIdx.x; i < br * x; i += blockDim.x) dst[i] = tile[i] / (float)P.n_keys;
 }

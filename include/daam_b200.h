@@ -49,9 +49,6 @@ enum daam_dtype { DAAM_F32 = 0, DAAM_F16 = 1, DAAM_BF16 = 2 };
 #define DAAM_ACC_RMW_LDST   0x10u /* coalesced load / add / store of the accumulator tile */
 #define DAAM_ACC_RMW_RED    0x20u /* red.global.add.f32 (SIMT) / bulk-async reduce-add from shared memory (MMA) */
 #define DAAM_ACC_NO_PDL     0x100u /* launch without programmatic dependent launch (measurement / debugging) */
-#define DAAM_ACC_RED_SEGMENTS 0x400u /* tcgen05 kernel, RED mode: 7 bulk-tensor reduce-adds of 11 token rows per tile */
-#define DAAM_ACC_RED_REGS   0x1000u /* tcgen05 kernel, RED mode: red.global.add.f32 from registers, no staging */
-#define DAAM_ACC_RED_ROWS   0x800u /* tcgen05 kernel, RED mode: 77 one-row bulk reduce-adds per tile (one per thread) */
 #define DAAM_ACC_EARLY_LOADS 0x200u /* The caller vouches that q and k of every layer were complete BEFORE the previous
                                      kernel on `stream` started (they were produced on another stream and joined through
                                      an event, or are resident inputs). Then only the kernel's accumulator updates wait

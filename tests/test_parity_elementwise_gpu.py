@@ -26,10 +26,7 @@ RTOL = {torch.float32: 1e-5, torch.float16: 1e-4, torch.bfloat16: 1e-4}
 ATOL = {torch.float32: 1e-6, torch.float16: 1e-5, torch.bfloat16: 1e-5}       # x steps
 
 PATHS = [('auto', _native.ACC_AUTO), ('simt', _native.ACC_FORCE_SIMT), ('mma', _native.ACC_FORCE_MMA),
-         ('mma-early', _native.ACC_FORCE_MMA | _native.ACC_EARLY_LOADS),
-         ('mma-seg', _native.ACC_FORCE_MMA | _native.ACC_RED_SEGMENTS),
-         ('mma-rows', _native.ACC_FORCE_MMA | _native.ACC_RED_ROWS | _native.ACC_EARLY_LOADS),
-         ('mma-regs', _native.ACC_FORCE_MMA | _native.ACC_RED_REGS | _native.ACC_EARLY_LOADS)]
+         ('mma-early', _native.ACC_FORCE_MMA | _native.ACC_EARLY_LOADS)]
 
 
 @pytest.fixture(autouse=True)

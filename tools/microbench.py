@@ -56,10 +56,7 @@ def main():
         'mma-ldst': _native.ACC_FORCE_MMA | _native.ACC_RMW_LDST,
         'mma-red-nopdl': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED | _native.ACC_NO_PDL,
         'mma-red-early': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED | _native.ACC_EARLY_LOADS,
-        'mma-seg-early': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED | _native.ACC_EARLY_LOADS | _native.ACC_RED_SEGMENTS,
-        'mma-regs-early': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED | _native.ACC_EARLY_LOADS | _native.ACC_RED_REGS,
         'mma-ldst-early': _native.ACC_FORCE_MMA | _native.ACC_RMW_LDST | _native.ACC_EARLY_LOADS,
-        'mma-rows-early': _native.ACC_FORCE_MMA | _native.ACC_RMW_RED | _native.ACC_EARLY_LOADS | _native.ACC_RED_ROWS,
     }
     if args.variants:
         variants = {k: v for k, v in variants.items() if k in args.variants}
