@@ -90,13 +90,22 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU. The bound is ~10 s of SM
+// clocks, far beyond any legitimate wait on a dedicated GPU; where a context can be descheduled for longer (MPS,
+// time-slicing, a debugger) build with -DDAAM_MBAR_TIMEOUT_CYCLES=0 to wait without a bound.
+#ifndef DAAM_MBAR_TIMEOUT_CYCLES
+#define DAAM_MBAR_TIMEOUT_CYCLES 20000000000LL
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
+#if DAAM_MBAR_TIMEOUT_CYCLES > 0
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 20000000000LL) __trap();    // ~10 s: far beyond any legitimate wait, preemption included
+    if (clock64() - t0 > DAAM_MBAR_TIMEOUT_CYCLES) __trap();
   }
+#else
+  while (!mbar_try(bar, parity)) {}
+#endif
 }
 
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
@@ -192,6 +201,15 @@ __device__ __forceinline__ Tile decode_tile(const LaunchParams& P, int tile, int
   return t;
 }
 
+// First tile whose weight offset (tiles before it x their weights) is >= w; total_tiles for w >= total_weight.
+__device__ __forceinline__ int tile_at_weight(const LaunchParams& P, long long w) {
+  if (w >= P.total_weight) return P.total_tiles;
+  int li = 0;
+  while (li + 1 < P.n_layers && w >= P.layer[li + 1].weight_begin) ++li;
+  const LayerParams& L = P.layer[li];
+  return L.tile_begin + (int)((w - L.weight_begin + L.weight - 1) / L.weight);
+}
+
 __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -246,9 +264,15 @@ accumulate_mma_kernel(const __grid_constant__ MmaParams MP) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + kOperandBytes + kPBytes + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per = P.total_tiles / gridDim.x, rem = P.total_tiles % gridDim.x;
-  const int first = blockIdx.x * per + min((int)blockIdx.x, rem);
-  const int count = per + ((int)blockIdx.x < rem ? 1 : 0);
+  int first, count;
+  if constexpr (!kChunked) {                           // equal tiles: contiguous ranges of per / per + 1 tiles
+    const int per = P.total_tiles / gridDim.x, rem = P.total_tiles % gridDim.x;
+    first = blockIdx.x * per + min((int)blockIdx.x, rem);
+    count = per + ((int)blockIdx.x < rem ? 1 : 0);
+  } else {                                             // tiles of several K-chunk counts: contiguous ranges of equal WEIGHT
+    first = tile_at_weight(P, (long long)P.total_weight * blockIdx.x / gridDim.x);
+    count = tile_at_weight(P, (long long)P.total_weight * (blockIdx.x + 1) / gridDim.x) - first;
+  }
 
   if (threadIdx.x == 0) {
 #pragma unroll

@@ -72,6 +72,8 @@ int make_layer_params(const daam_layer& in, int index, LayerParams* out, bool ne
   L.tile_begin = 0;
   const size_t es = dtype_size(in.dtype);
   auto aligned = [&](long long stride) { return (stride * (long long)es) % 16 == 0; };
+  L.weight = 1;
+  L.weight_begin = 0;
   L.vec_ok = reinterpret_cast<uintptr_t>(in.q) % 16 == 0 && reinterpret_cast<uintptr_t>(in.k) % 16 == 0 &&
              aligned(in.q_stride_prompt) && aligned(in.q_stride_pixel) && aligned(in.q_stride_head) &&
              aligned(in.k_stride_prompt) && aligned(in.k_stride_token) && aligned(in.k_stride_head);
@@ -117,7 +119,7 @@ int build_plan(const daam_layer* layers, int n_layers, uint32_t flags, const Dev
     p.rmw_mode = (rmw == DAAM_ACC_RMW_LDST) ? 0 : 1;     // default: reduce-add
     p.pdl = (flags & DAAM_ACC_NO_PDL) ? 0 : 1;
     p.early_loads = (flags & DAAM_ACC_EARLY_LOADS) && p.pdl ? 1 : 0;
-    p.pad_ = 0;
+    p.total_weight = 0;
   }
   auto close = [&](int which) -> int {
     LaunchParams& p = packs[which];
@@ -135,6 +137,7 @@ int build_plan(const daam_layer* layers, int n_layers, uint32_t flags, const Dev
     }
     p.n_layers = 0;
     p.total_tiles = 0;
+    p.total_weight = 0;
     return rc;
   };
   for (int i = 0; i < n_layers; ++i) {
@@ -149,8 +152,15 @@ int build_plan(const daam_layer* layers, int n_layers, uint32_t flags, const Dev
     const int which = use_mma ? (L.dtype == DAAM_F32 ? 1 : 0) : 2;
     LaunchParams& p = packs[which];
     L.tile_begin = p.total_tiles;
+    // Cost of a tile relative to the launch's other layers. Every 64-wide K chunk is one load -> (convert ->) MMA
+    // round: in the fp32 split form that chain is the tile's cost; in the 16-bit form the chunks are cheap next to the
+    // tile's fixed 77 x 128 accumulator update (two units).
+    const int n_chunks = (L.head_dim + 63) / 64;
+    L.weight = which == 1 ? n_chunks : 2 + n_chunks;
+    L.weight_begin = p.total_weight;
     p.layer[p.n_layers++] = L;
     p.total_tiles += L.tiles_per_head * L.heads * L.n_prompts;
+    p.total_weight += L.tiles_per_head * L.heads * L.n_prompts * L.weight;
     if (p.n_layers == kMaxLayersPerLaunch)
       if (int rc = close(which)) return rc;
   }

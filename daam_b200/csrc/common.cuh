@@ -28,6 +28,8 @@ struct LayerParams {
   int tiles_per_head;       // ceil(hw / kTilePixels)
   int tile_begin;
   int vec_ok;               // 1: q/k rows are 16-byte aligned -> vector loads
+  int weight;               // relative cost of one tile of this layer (tcgen05 kernel, K-chunked launches)
+  int weight_begin;         // exclusive prefix of tiles x weight over the launch's layers
   int pad_;
 };
 
@@ -37,7 +39,7 @@ struct LaunchParams {
   int rmw_mode;             // 0: load/add/store, 1: reduce-add
   int pdl;                  // 1: launch with programmatic stream serialization (prologue overlaps the previous kernel)
   int early_loads;          // 1: only the accumulator updates wait for the previous kernel (DAAM_ACC_EARLY_LOADS)
-  int pad_;
+  int total_weight;         // sum of tiles x weight (K-chunked launches partition by weight, not by tile count)
   LayerParams layer[kMaxLayersPerLaunch];
 };
 

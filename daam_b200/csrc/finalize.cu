@@ -179,15 +179,17 @@ __device__ __forceinline__ void class_pass(const FinalizeParams& P, int side, in
   const int row_units = side / 4, key_units = VR * row_units;     // 16-byte units
   const int sy0 = band * R;
 
+  // copy duty of this thread, fixed for the class: one 16-byte unit (row vr, column 4 * c4) of every keys_par-th key
+  const int keys_par = 256 / key_units, copy_k = (int)threadIdx.x / key_units;
+  const int copy_pos = (int)threadIdx.x - copy_k * key_units;
+  const int copy_vr = copy_pos / row_units, copy_c4 = copy_pos - copy_vr * row_units;
+  const int copy_dst = copy_vr * side + 4 * copy_c4;
+  const int copy_src = min(max(sy0 - 2 + copy_vr, 0), side - 1) * side + 4 * copy_c4;   // border rows replicate, as the taps clamp
   auto issue = [&](int c) {
-    float* buf = stage + (c & 1) * kStageFloats;
+    float* buf = stage + (c & 1) * kStageFloats + copy_dst;
     const int k0 = c * kc, kn = min(kc, nk - k0);
-    for (int u = threadIdx.x; u < kn * key_units; u += blockDim.x) {
-      const int k = u / key_units, rem = u - k * key_units;
-      const int vr = rem / row_units, c4 = rem - vr * row_units;
-      const int row = min(max(sy0 - 2 + vr, 0), side - 1);          // border rows are replicated, as the taps clamp
-      cp_async16(buf + k * region + vr * side + 4 * c4, keys[k0 + k] + row * side + 4 * c4);
-    }
+    if (copy_k < keys_par)
+      for (int k = copy_k; k < kn; k += keys_par) cp_async16(buf + k * region, keys[k0 + k] + copy_src);
     cp_async_commit();
   };
 
@@ -225,22 +227,29 @@ __device__ __forceinline__ void class_pass(const FinalizeParams& P, int side, in
     }
     __syncthreads();                                   // buffer (c & 1) may be overwritten by chunk c + 2
   }
-  for (int g = 0; g < kg; ++g) {                       // merge the key groups in a fixed order
-    if (live && group == g) {
-      const int oy0 = ly * F, ox0 = sx * F;
+  // merge the key groups in a fixed order (deterministic sums): every group parks its band in the (now free) first
+  // chunk buffer, then each band element is summed over the groups by one thread
+  const int band_elems = br * x;
+  if (live) {
+    float* mine = stage + group * band_elems + (ly * F) * x + sx * F;
 #pragma unroll
-      for (int py = 0; py < F; ++py)
+    for (int py = 0; py < F; ++py)
 #pragma unroll
-        for (int px = 0; px < F; ++px) tile[(oy0 + py) * x + ox0 + px] += acc[py][px];
-    }
-    __syncthreads();
+      for (int px = 0; px < F; ++px) mine[py * x + px] = acc[py][px];
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < band_elems; i += blockDim.x) {
+    float sum = tile[i];
+    for (int g = 0; g < kg; ++g) sum += stage[g * band_elems + i];
+    tile[i] = sum;
+  }
+  __syncthreads();
 }
 
 // factor 1: bicubic at scale 1 is the identity, the class contributes clamp(src) -- coalesced float4 reads; when the
 // band has fewer float4s than threads, the spare thread groups take every kg-th key (merged in a fixed order)
 __device__ __forceinline__ void class_pass_identity(const FinalizeParams& P, int nk, int band, int br, float* tile,
-                                                    const float* const* keys) {
+                                                    const float* const* keys, float* stage) {
   const int x = P.x;
   const int n4 = br * x / 4;
   const int kg = n4 >= 256 ? 1 : 256 / n4;
@@ -258,12 +267,21 @@ __device__ __forceinline__ void class_pass_identity(const FinalizeParams& P, int
         acc.x += fmaxf(v.x, 0.f); acc.y += fmaxf(v.y, 0.f); acc.z += fmaxf(v.z, 0.f); acc.w += fmaxf(v.w, 0.f);
       }
     }
-    for (int g = 0; g < kg; ++g) {
-      if (live && group == g) {
+    if (kg == 1) {                                       // every float4 of the band has one owner
+      if (live) {
         float4* dst = reinterpret_cast<float4*>(tile + 4 * i);
         float4 cur = *dst;
         cur.x += acc.x; cur.y += acc.y; cur.z += acc.z; cur.w += acc.w;
         *dst = cur;
+      }
+      __syncthreads();
+    } else {                                             // park the groups' bands, then sum them in a fixed order
+      if (live) *reinterpret_cast<float4*>(stage + group * (br * x) + 4 * i) = acc;
+      __syncthreads();
+      for (int e = threadIdx.x; e < br * x; e += blockDim.x) {
+        float sum = tile[e];
+        for (int g = 0; g < kg; ++g) sum += stage[g * (br * x) + e];
+        tile[e] = sum;
       }
       __syncthreads();
     }
@@ -300,7 +318,7 @@ __global__ void __launch_bounds__(256, 2) finalize_fast_kernel(const __grid_cons
   for (int c = 0; c < C.n; ++c) {
     const int side = C.side[c], f = x / side, nk = C.key_begin[c + 1] - C.key_begin[c];
     const float* const* ck = keys + C.key_begin[c];
-    if (f == 1) class_pass_identity(P, nk, band, br, tile, ck);
+    if (f == 1) class_pass_identity(P, nk, band, br, tile, ck, stage);
     else if (f == 2) class_pass<2>(P, side, nk, band, br, tile, ck, stage);
     else class_pass<4>(P, side, nk, band, br, tile, ck, stage);
   }

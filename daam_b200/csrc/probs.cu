@@ -110,6 +110,7 @@ extern "C" int daam_attention_probs(const daam_layer* layer, void* probs, void* 
   p.rmw_mode = 0;
   p.pdl = 0;
   p.early_loads = 0;
+  p.total_weight = p.total_tiles;
   size_t floats = simt::tile_smem_floats(p.layer[0].head_dim);
   const size_t need = (size_t)p.layer[0].head_dim * kTokensPad + (size_t)kTilePixels * kTokens;   // K^T + staged P
   if (need > floats) floats = need;

@@ -1,5 +1,5 @@
 #!/bin/bash
-TAG=${1:-r02e}
+TAG=${1:-r02}
 mkdir -p gpurun_out
 echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -8 | tee gpurun_out/${TAG}_pytest.txt
 echo "== microbench"; timeout 300 python tools/microbench.py --workload sd21 --dtypes bf16 fp32 --prompts 1 8 --variants mma-red-early 2>&1 | grep -v "per_layer\": true" | tail -4
