@@ -224,3 +224,50 @@ def test_plan_cache_replays_and_invalidates():
     one = oracle_layer_maps(qa, k, heads, 0.125)
     for a in (accs[0], accs[17], accs[39]):
         assert_elementwise(a[0], 2 * one, 1e-4, 2e-5, 'evicted plans')
+
+
+def test_early_loads_back_to_back_is_bit_identical_to_serialised_launches():
+    """DAAM_ACC_EARLY_LOADS lets a launch's loads, MMAs and first softmax overlap the previous launch's tail; only the
+    accumulator updates wait for it. The order of updates per element is unchanged, so 30 back-to-back launches on the
+    same slabs must equal the serialised (no-PDL) sequence bit for bit, for both operand classes."""
+    g = torch.Generator().manual_seed(17)
+    for dtype in (torch.bfloat16, torch.float32):
+        shapes = [(1024, 10), (256, 20), (4096, 5)]
+        qs = [[torch.randn(2, hw, h * 64, generator=g).to(dtype).to(DEV) for hw, h in shapes] for _ in range(3)]
+        ks = [[torch.randn(2, 77, h * 64, generator=g).to(dtype).to(DEV) for hw, h in shapes] for _ in range(3)]
+        results = []
+        for flags in (_native.ACC_NO_PDL, _native.ACC_EARLY_LOADS, _native.ACC_AUTO):
+            accs = [ops.new_accumulator(1, h, hw, DEV) for hw, h in shapes]
+            packs = [ops.pack([ops.make_layer_desc(q, k, a, h, 0.125) for q, k, a, (hw, h) in zip(qs[i], ks[i], accs, shapes)])
+                     for i in range(3)]
+            torch.cuda.synchronize()
+            for step in range(30):
+                ops.accumulate(packs[step % 3], DEV, flags=flags)
+            torch.cuda.synchronize()
+            results.append(accs)
+        for a, b, c in zip(*results):
+            assert torch.equal(a, b) and torch.equal(a, c)
+        sums = results[1][0].double().sum(dim=(2, 3))
+        assert torch.allclose(sums, torch.full_like(sums, 30.0 * shapes[0][0]), rtol=2e-5)
+
+
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32])
+def test_weighted_partition_of_mixed_head_dims(dtype):
+    """One launch with 1-, 2-, 3- and 4-chunk layers of very different tile counts (the K-chunked instances partition by
+    weight, some CTAs get no tile at all): every layer against the oracle, nothing outside the slabs touched."""
+    g = torch.Generator().manual_seed(23)
+    cases = [(16, 2, 256), (4096, 2, 40), (64, 3, 192), (1024, 1, 80), (256, 8, 160), (144, 2, 64), (16, 1, 8)]
+    qs, ks, slabs, descs = [], [], [], []
+    for hw, heads, d in cases:
+        q = torch.randn(2, hw, heads * d, generator=g).to(dtype).to(DEV)
+        k = torch.randn(2, 77, heads * d, generator=g).to(dtype).to(DEV)
+        slab = torch.zeros(heads + 2, 77, hw, device=DEV)                # guard heads before and after
+        qs.append(q), ks.append(k), slabs.append(slab)
+        descs.append(ops.make_layer_desc(q, k, slab[1:-1].unsqueeze(0), heads, d ** -0.5))
+    for rep in range(2):
+        ops.accumulate(descs, DEV, flags=_native.ACC_FORCE_MMA | _native.ACC_EARLY_LOADS)
+    torch.cuda.synchronize()
+    for (hw, heads, d), q, k, slab in zip(cases, qs, ks, slabs):
+        ref = 2 * oracle_layer_maps(q, k, heads, d ** -0.5)
+        assert_elementwise(slab[1:-1], ref, RTOL[dtype], 2 * ATOL[dtype], f'hw{hw} H{heads} d{d}')
+        assert float(slab[0].abs().max()) == 0.0 and float(slab[-1].abs().max()) == 0.0

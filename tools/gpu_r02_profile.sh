@@ -19,11 +19,11 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:accu
 tail -1 gpurun_out/${TAG}_ncu_full.log | cut -c1-200
 echo "== ncu full: accumulate, fp32 split form"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:accumulate_mma -s 30 -c 1 -f -o gpurun_out/${TAG}_prof_fp32 \
-  python tools/microbench.py --workload sd21 --dtypes fp32 --prompts 1 --variants mma-red-early > gpurun_out/${TAG}_ncu_fp32.log 2>&1
+  python tools/microbench.py --no-save --workload sd21 --dtypes fp32 --prompts 1 --variants mma-red-early > gpurun_out/${TAG}_ncu_fp32.log 2>&1
 tail -1 gpurun_out/${TAG}_ncu_fp32.log | cut -c1-200
 echo "== DRAM traffic per launch: steady state (no cache control) and isolated"
 M="--metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:accumulate_mma -s 60 -c 10 --csv"
-timeout 600 ncu $M --cache-control none --log-file gpurun_out/${TAG}_traffic_steady.csv python tools/microbench.py --workload sd21 --dtypes bf16 --prompts 1 --variants mma-red-early > /dev/null 2>&1
-timeout 600 ncu $M --log-file gpurun_out/${TAG}_traffic_isolated.csv python tools/microbench.py --workload sd21 --dtypes bf16 --prompts 1 --variants mma-red-early > /dev/null 2>&1
+timeout 600 ncu $M --cache-control none --log-file gpurun_out/${TAG}_traffic_steady.csv python tools/microbench.py --no-save --workload sd21 --dtypes bf16 --prompts 1 --variants mma-red-early > /dev/null 2>&1
+timeout 600 ncu $M --log-file gpurun_out/${TAG}_traffic_isolated.csv python tools/microbench.py --no-save --workload sd21 --dtypes bf16 --prompts 1 --variants mma-red-early > /dev/null 2>&1
 tail -4 gpurun_out/${TAG}_traffic_steady.csv | cut -c1-300
 ls -la gpurun_out | grep ${TAG}

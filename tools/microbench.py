@@ -46,6 +46,7 @@ def main():
     ap.add_argument('--prompts', type=int, nargs='+', default=[1, 8])
     ap.add_argument('--dtypes', nargs='+', default=['bf16', 'fp32'])   # fp32: mma-* = split (2 x tf32) form
     ap.add_argument('--variants', nargs='+', default=None)
+    ap.add_argument('--no-save', action='store_true', help='do not write gpurun_out/microbench_*.json (runs under ncu)')
     args = ap.parse_args()
     peak, _ = measured_peak()
     layers = traced_layers(args.workload)
@@ -81,6 +82,8 @@ def main():
                     print(json.dumps(row), flush=True)
             del sets
             torch.cuda.empty_cache()
+    if args.no_save:
+        return
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', f'microbench_{args.workload}_{"-".join(args.dtypes)}.json'), 'w') as f:
         json.dump(rows, f, indent=1)
