@@ -164,34 +164,55 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Streams chunk `chunk` of a factor-2 / factor-4 class into `buf` (one commit group): the band's source rows (+2 halo rows
+// each side, border rows replicated like the clamped taps) of up to kc keys. Every thread copies one fixed 16-byte unit
+// of every keys_par-th key. Shared by the class passes and by the cross-class prefetch (next class's first chunk).
+struct ChunkGeom {
+  int region, kc, n_src, kg, VR;
+  __device__ __forceinline__ ChunkGeom(int side, int f, int br) {
+    const int R = br / f;                              // source rows under the band
+    VR = R + 4;                                        // + 2 halo rows above and below
+    region = VR * side;                                // floats of one key's staged rows
+    n_src = R * side;                                  // source pixels under the band (<= 256, checked by the host)
+    kg = 256 / n_src;                                  // thread groups that split the keys
+    kc = kStageFloats / region;                        // keys per chunk, a multiple of kg so every group keeps its stride
+    kc -= kc % kg;
+  }
+};
+__device__ __forceinline__ void issue_chunk(int side, int f, int band, int br, const float* const* keys, int nk, int chunk,
+                                            float* buf) {
+  const ChunkGeom G(side, f, br);
+  const int row_units = side / 4, key_units = G.VR * row_units;     // 16-byte units
+  const int keys_par = 256 / key_units, copy_k = (int)threadIdx.x / key_units;
+  const int k0 = chunk * G.kc, kn = min(G.kc, nk - k0);
+  if (copy_k < keys_par) {
+    const int pos = (int)threadIdx.x - copy_k * key_units;
+    const int vr = pos / row_units, c4 = pos - vr * row_units;
+    const int src = min(max(band * (br / f) - 2 + vr, 0), side - 1) * side + 4 * c4;
+    float* dst = buf + vr * side + 4 * c4;
+    for (int k = copy_k; k < kn; k += keys_par) cp_async16(dst + k * G.region, keys[k0 + k] + src);
+  }
+  cp_async_commit();
+}
+
+// What to prefetch while a class is being merged: the first chunk of the next factor-2 / factor-4 class (into chunk
+// buffer 1; the merge parks the key groups in buffer 0).
+struct NextClass {
+  int side, f, nk;                                     // f == 0: nothing to prefetch
+  const float* const* keys;
+};
+
+// `first_buf`: the chunk buffer holding this class's chunk 0 (1 when the previous class prefetched it, else 0 and the
+// chunk is issued here).
 template <int F>
 __device__ __forceinline__ void class_pass(const FinalizeParams& P, int side, int nk, int band, int br, float* tile,
-                                           const float* const* keys, float* stage) {
+                                           const float* const* keys, float* stage, bool prefetched, const NextClass& next) {
   const int x = P.x;
-  const int R = br / F;                                // source rows under this band
-  const int VR = R + 4;                                // + 2 halo rows above and below
-  const int region = VR * side;                        // floats of one key's staged rows
-  const int n_src = R * side;                          // source pixels under the band (<= 256, checked by the host)
-  const int kg = 256 / n_src;                          // thread groups that split the keys
-  int kc = kStageFloats / region;                      // keys per chunk, a multiple of kg so every group keeps its stride
-  kc -= kc % kg;
+  const ChunkGeom G(side, F, br);
+  const int region = G.region, n_src = G.n_src, kg = G.kg, kc = G.kc;
   const int n_chunks = (nk + kc - 1) / kc;
-  const int row_units = side / 4, key_units = VR * row_units;     // 16-byte units
-  const int sy0 = band * R;
-
-  // copy duty of this thread, fixed for the class: one 16-byte unit (row vr, column 4 * c4) of every keys_par-th key
-  const int keys_par = 256 / key_units, copy_k = (int)threadIdx.x / key_units;
-  const int copy_pos = (int)threadIdx.x - copy_k * key_units;
-  const int copy_vr = copy_pos / row_units, copy_c4 = copy_pos - copy_vr * row_units;
-  const int copy_dst = copy_vr * side + 4 * copy_c4;
-  const int copy_src = min(max(sy0 - 2 + copy_vr, 0), side - 1) * side + 4 * copy_c4;   // border rows replicate, as the taps clamp
-  auto issue = [&](int c) {
-    float* buf = stage + (c & 1) * kStageFloats + copy_dst;
-    const int k0 = c * kc, kn = min(kc, nk - k0);
-    if (copy_k < keys_par)
-      for (int k = copy_k; k < kn; k += keys_par) cp_async16(buf + k * region, keys[k0 + k] + copy_src);
-    cp_async_commit();
-  };
+  const int first_buf = prefetched ? 1 : 0;
+  auto issue = [&](int c) { issue_chunk(side, F, band, br, keys, nk, c, stage + ((c + first_buf) & 1) * kStageFloats); };
 
   const int group = (int)threadIdx.x / n_src;
   const int s = (int)threadIdx.x - group * n_src;
@@ -208,12 +229,12 @@ __device__ __forceinline__ void class_pass(const FinalizeParams& P, int side, in
 #pragma unroll
     for (int px = 0; px < F; ++px) acc[py][px] = 0.f;
 
-  if (n_chunks > 0) issue(0);
+  if (!prefetched) issue(0);
   for (int c = 0; c < n_chunks; ++c) {
     if (c + 1 < n_chunks) { issue(c + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();                                   // chunk c has landed for every thread
     if (live) {
-      const float* buf = stage + (c & 1) * kStageFloats + ly * side;
+      const float* buf = stage + ((c + first_buf) & 1) * kStageFloats + ly * side;
       const int kn = min(kc, nk - c * kc);
       for (int k = group; k < kn; k += kg) {
         const float* src = buf + k * region;
@@ -227,6 +248,8 @@ __device__ __forceinline__ void class_pass(const FinalizeParams& P, int side, in
     }
     __syncthreads();                                   // buffer (c & 1) may be overwritten by chunk c + 2
   }
+  // both chunk buffers are free now: the next class's first chunk streams into buffer 1 while this class is merged
+  if (next.f) issue_chunk(next.side, next.f, band, br, next.keys, next.nk, 0, stage + kStageFloats);
   // merge the key groups in a fixed order (deterministic sums): every group parks its band in the (now free) first
   // chunk buffer, then each band element is summed over the groups by one thread
   const int band_elems = br * x;
@@ -249,8 +272,10 @@ __device__ __forceinline__ void class_pass(const FinalizeParams& P, int side, in
 // factor 1: bicubic at scale 1 is the identity, the class contributes clamp(src) -- coalesced float4 reads; when the
 // band has fewer float4s than threads, the spare thread groups take every kg-th key (merged in a fixed order)
 __device__ __forceinline__ void class_pass_identity(const FinalizeParams& P, int nk, int band, int br, float* tile,
-                                                    const float* const* keys, float* stage) {
+                                                    const float* const* keys, float* stage, const NextClass& next) {
   const int x = P.x;
+  // this pass reads its keys straight from global memory: the next class's first chunk streams in underneath it
+  if (next.f) issue_chunk(next.side, next.f, band, br, next.keys, next.nk, 0, stage + kStageFloats);
   const int n4 = br * x / 4;
   const int kg = n4 >= 256 ? 1 : 256 / n4;
   const int passes = (n4 + 255) / 256;
@@ -315,12 +340,17 @@ __global__ void __launch_bounds__(256, 2) finalize_fast_kernel(const __grid_cons
   }
   for (int i = threadIdx.x; i < br * x; i += blockDim.x) tile[i] = 0.f;
   __syncthreads();
+  bool prefetched = false;                             // chunk 0 of class c is already streaming into buffer 1
   for (int c = 0; c < C.n; ++c) {
     const int side = C.side[c], f = x / side, nk = C.key_begin[c + 1] - C.key_begin[c];
     const float* const* ck = keys + C.key_begin[c];
-    if (f == 1) class_pass_identity(P, nk, band, br, tile, ck, stage);
-    else if (f == 2) class_pass<2>(P, side, nk, band, br, tile, ck, stage);
-    else class_pass<4>(P, side, nk, band, br, tile, ck, stage);
+    NextClass next = {0, 0, 0, nullptr};
+    if (c + 1 < C.n && C.side[c + 1] != x)
+      next = {C.side[c + 1], x / C.side[c + 1], C.key_begin[c + 2] - C.key_begin[c + 1], keys + C.key_begin[c + 1]};
+    if (f == 1) class_pass_identity(P, nk, band, br, tile, ck, stage, next);
+    else if (f == 2) class_pass<2>(P, side, nk, band, br, tile, ck, stage, prefetched, next);
+    else class_pass<4>(P, side, nk, band, br, tile, ck, stage, prefetched, next);
+    prefetched = next.f != 0;
   }
   __syncthreads();
   float* dst = out + (long long)t * x * x + (long long)band * br * x;
