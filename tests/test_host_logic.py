@@ -202,6 +202,33 @@ def test_bench_workload_definitions_match_the_survey():
     sd15 = bench.traced_layers('sd15')
     assert len(sd15) == 15 and {h for _, h, _ in sd15} == {8} and {d for _, _, d in sd15} == {40, 80, 160}
     assert bench.px_per_step(sd21, n_prompts=8) == 8 * 13_798_400
+    # BASELINE config 5, "all 70 cross-attn layers traced": SURVEY.md 8d gives 126.2 Mpx and 1 231.7 MB per step and prompt
+    sdxl70 = bench.traced_layers('sdxl70')
+    assert len(sdxl70) == 70 and sdxl70[:60] == sdxl
+    assert abs(bench.px_per_step(sdxl70) / 1e6 - 126.2) < 0.1
+    assert abs(bench.algorithmic_bytes_per_step(sdxl70, esize=2) / 1e6 - 1231.7) < 0.5
+
+
+def test_bench_config_is_identical_for_both_arms_and_located_layers_match_the_workloads():
+    """The `config` object both bench arms emit comes from one function; the layer lists the bench assumes are what the
+    locator finds on the synthetic SDXL tree (60 by default, 70 with the mid block, reference: daam/hook.py:110-114)."""
+    import argparse
+    import bench
+    from daam_b200.locate import UNetCrossAttentionLocator
+    from daam_b200.testing.synthetic import SDXL_SPEC, SyntheticUNet
+    args = argparse.Namespace(workload='sdxl70', prompts=2, dtype='fp16', steps=30)
+    cfg = bench.shared_config(args, bench.traced_layers('sdxl70'), 8)
+    assert cfg == bench.shared_config(args, bench.traced_layers('sdxl70'), 8)
+    assert 'all 70 cross-attn layers' in cfg['workload'] and cfg['parallelism'].endswith('dp8')
+    assert cfg['px_per_step'] == 2 * bench.px_per_step(bench.traced_layers('sdxl70'))
+    with torch.device('meta'):
+        unet = SyntheticUNet(SDXL_SPEC, body='skeleton')
+    assert len(UNetCrossAttentionLocator().locate(unet)) == 60
+    located = UNetCrossAttentionLocator(locate_middle_block=True).locate(unet)
+    assert len(located) == 70
+    shapes = [(m.heads, m.to_q.in_features) for m in located]
+    # up blocks first (1280-wide x 30, 640-wide x 6), then down (640 x 4, 1280 x 20), the mid block last
+    assert shapes == [(20, 1280)] * 30 + [(10, 640)] * 6 + [(10, 640)] * 4 + [(20, 1280)] * 20 + [(20, 1280)] * 10
 
 
 def test_bench_clock_sampler_and_stdout_contract(capfd):
