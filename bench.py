@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the cross-attention heat-map hot path (BASELINE.json metric: heat-map px/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload sd21|sdxl|sdxl70|sd15] [--prompts P]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload sd21|sd21_768|sdxl|sdxl70|sd15] [--prompts P]
 
 Workload (BASELINE.json configs[1]): random-init SD-2.1-base UNet shapes, 64x64 latent, 77 tokens, bf16, the 15 traced
 cross-attention layers of one denoising step. A bench "step" is one pass of the hot path over one step's Q/K:
@@ -74,6 +74,9 @@ def traced_layers(workload: str):
     if workload == 'sd21':
         shapes = [(256, 20)] * 3 + [(1024, 10)] * 3 + [(4096, 5)] * 3 + [(4096, 5)] * 2 + [(1024, 10)] * 2 + [(256, 20)] * 2
         return [(hw, h, 64) for hw, h in shapes]
+    if workload == 'sd21_768':   # the 768-pixel SD-2.1: 96x96 latent, 9216 / 2304 / 576 query positions (partial 128-pixel tiles)
+        shapes = [(576, 20)] * 3 + [(2304, 10)] * 3 + [(9216, 5)] * 3 + [(9216, 5)] * 2 + [(2304, 10)] * 2 + [(576, 20)] * 2
+        return [(hw, h, 64) for hw, h in shapes]
     if workload == 'sdxl':   # 60 layers (default trace, no mid block): up 3x10 @32^2, 3x2 @64^2; down 2x2 @64^2, 2x10 @32^2
         shapes = [(1024, 20)] * 30 + [(4096, 10)] * 6 + [(4096, 10)] * 4 + [(1024, 20)] * 20
         return [(hw, h, 64) for hw, h in shapes]
@@ -91,7 +94,8 @@ def px_per_step(layers, n_prompts=1):
     return n_prompts * sum(h * TOKENS * hw for hw, h, _ in layers)
 
 
-def literal_px_per_step(layers, n_prompts=1, x=64):
+def literal_px_per_step(layers, n_prompts=1, x=None):
+    x = x or (96 if max(hw for hw, _, _ in layers) == 9216 else 64)
     return n_prompts * len(layers) * TOKENS * x * x      # BASELINE-literal "layers x tokens x 64^2"
 
 
@@ -532,14 +536,15 @@ def run_reference(args):
 
 
 def workload_spec(workload):
-    from daam_b200.testing.synthetic import SD15_SPEC, SD21_SPEC, SDXL_SPEC
-    return {'sd21': SD21_SPEC, 'sdxl': SDXL_SPEC, 'sdxl70': SDXL_SPEC, 'sd15': SD15_SPEC}[workload]
+    from daam_b200.testing.synthetic import SD15_SPEC, SD21_768_SPEC, SD21_SPEC, SDXL_SPEC
+    return {'sd21': SD21_SPEC, 'sd21_768': SD21_768_SPEC, 'sdxl': SDXL_SPEC, 'sdxl70': SDXL_SPEC, 'sd15': SD15_SPEC}[workload]
 
 
 def workload_name(args):
     base = {'sd15': 'random-init SD-1.5 UNet shapes (8 heads, head dims 40/80/160), 64x64 latent, 77 tokens, 15 traced '
                     'cross-attn layers/step',
             'sd21': 'random-init SD-2.1-base UNet shapes, 64x64 latent, 77 tokens, 15 traced cross-attn layers/step',
+            'sd21_768': 'random-init SD-2.1 (768-pixel) UNet shapes, 96x96 latent, 77 tokens, 15 traced cross-attn layers/step',
             'sdxl': 'random-init SDXL UNet shapes, 128x128 latent, 77 tokens, 60 traced cross-attn layers/step',
             'sdxl70': 'random-init SDXL UNet shapes, 128x128 latent, 77 tokens, all 70 cross-attn layers traced/step '
                       '(mid block included)'}
@@ -575,7 +580,7 @@ def main():
     ap.add_argument('--steps', type=int, default=50)       # BASELINE configs[1]: 50 denoising steps
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='daam_b200', choices=['daam_b200', 'reference'])
-    ap.add_argument('--workload', default='sd21', choices=['sd21', 'sdxl', 'sdxl70', 'sd15'])
+    ap.add_argument('--workload', default='sd21', choices=['sd21', 'sd21_768', 'sdxl', 'sdxl70', 'sd15'])
     ap.add_argument('--prompts', type=int, default=1, help='prompts per GPU traced together (batch_prompts mode)')
     ap.add_argument('--dtype', default=None, choices=['bf16', 'fp16', 'fp32'])
     ap.add_argument('--ref-device', default='cpu', choices=['cpu', 'cuda'],
@@ -586,7 +591,7 @@ def main():
     ap.add_argument('--skip-e2e', action='store_true', help='kernel legs only (profiling runs)')
     args = ap.parse_args()
     if args.dtype is None:   # sd15: the reference's default load
-        args.dtype = {'sd21': 'bf16', 'sdxl': 'fp16', 'sdxl70': 'fp16', 'sd15': 'fp32'}[args.workload]
+        args.dtype = {'sd21': 'bf16', 'sd21_768': 'bf16', 'sdxl': 'fp16', 'sdxl70': 'fp16', 'sd15': 'fp32'}[args.workload]
     args.warmup = max(3, args.warmup)
     capture_stdout()
 

@@ -31,7 +31,7 @@ import torch.nn.functional as F
 
 __all__ = [
     'SyntheticAttention', 'SDPAProcessor', 'SyntheticUNet', 'SyntheticPipeline', 'WhitespaceTokenizer',
-    'UNetSpec', 'SD21_SPEC', 'SDXL_SPEC', 'SD15_SPEC', 'TINY_SPEC', 'TINY15_SPEC', 'TINY96_SPEC', 'make_pipeline',
+    'UNetSpec', 'SD21_SPEC', 'SD21_768_SPEC', 'SDXL_SPEC', 'SD15_SPEC', 'TINY_SPEC', 'TINY15_SPEC', 'TINY96_SPEC', 'make_pipeline',
 ]
 
 
@@ -306,6 +306,8 @@ class UNetSpec:
 
 # public unet/config.json values of stabilityai/stable-diffusion-2-1-base and stabilityai/stable-diffusion-xl-base-1.0
 SD21_SPEC = UNetSpec('sd21-base', 64, (320, 640, 1280, 1280), (5, 10, 20, 20), (1, 1, 1, 0), 1024)
+# stabilityai/stable-diffusion-2-1 (the 768-pixel v-prediction model): same UNet, 96x96 latent -> latent_hw 9216
+SD21_768_SPEC = UNetSpec('sd21-768', 96, (320, 640, 1280, 1280), (5, 10, 20, 20), (1, 1, 1, 0), 1024)
 SDXL_SPEC = UNetSpec('sdxl-base', 128, (320, 640, 1280), (5, 10, 20), (0, 2, 10), 2048, mid_depth=10)
 # runwayml/stable-diffusion-v1-5: 8 heads at every level, head dims 40 / 80 / 160
 SD15_SPEC = UNetSpec('sd15', 64, (320, 640, 1280, 1280), (8, 8, 8, 8), (1, 1, 1, 0), 768, dim_head=None)
