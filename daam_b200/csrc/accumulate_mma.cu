@@ -603,15 +603,15 @@ struct PreparedMma {
   MmaParams mp;
   int grid, block, smem, variant;                     // variant: bit 0 split (fp32), bit 1 chunked (head_dim > 64)
 };
-size_t prepared_mma_size() { return sizeof(PreparedMma); }
+void* prepared_mma_new() { return new PreparedMma; }                 // (aligned new: CUtensorMap is alignas(64))
+void prepared_mma_delete(void* p) { delete static_cast<PreparedMma*>(p); }
 
 bool mma_supported(const LayerParams& L) {
   return L.head_dim % 8 == 0 && L.head_dim <= DAAM_MAX_HEAD_DIM && L.vec_ok && L.qs_head > 0 && L.qs_pixel > 0 &&
          L.ks_head > 0 && L.ks_token > 0;
 }
 
-// Tensor maps, grid and kernel variant of one pack of layers (all fp32, or all 16-bit). `out` points at
-// prepared_mma_size() bytes owned by the caller.
+// Tensor maps, grid and kernel variant of one pack of layers (all fp32, or all 16-bit). `out`: prepared_mma_new().
 int prepare_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, void* out) {
   if (dev.cc_major != 10) { set_error("the tcgen05 kernel needs an sm_100 device (found sm_%d%d)", dev.cc_major, dev.cc_minor); return DAAM_E_UNSUPPORTED; }
   PreparedMma& pm = *static_cast<PreparedMma*>(out);

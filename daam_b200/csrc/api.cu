@@ -94,7 +94,8 @@ struct PlannedLaunch {
   LaunchParams simt;                     // SIMT: the parameter block itself
   int grid = 0;
   size_t smem = 0;
-  std::unique_ptr<uint8_t[]> mma;        // tcgen05: PreparedMma (tensor maps + parameter block)
+  struct MmaDeleter { void operator()(void* p) const { prepared_mma_delete(p); } };
+  std::unique_ptr<void, MmaDeleter> mma; // tcgen05: PreparedMma (tensor maps + parameter block), opaque here
 };
 
 // Everything daam_accumulate derives from its input: the packs, their tensor maps, grids. A trace replays the same
@@ -132,7 +133,7 @@ int build_plan(const daam_layer* layers, int n_layers, uint32_t flags, const Dev
     l.is_mma = which != 2;
     int rc;
     if (l.is_mma) {
-      l.mma.reset(new uint8_t[prepared_mma_size()]);
+      l.mma.reset(prepared_mma_new());
       rc = prepare_accumulate_mma(p, dev, l.mma.get());
     } else {
       l.simt = p;

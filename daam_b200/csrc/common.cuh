@@ -72,7 +72,8 @@ void count_launch(int n = 1);
 // distinct daam_layer[] input: the steady state of a trace replays the same layer calls every denoising step.
 int prepare_accumulate_simt(const LaunchParams& p, const DeviceInfo& dev, int* grid, size_t* smem);
 int launch_prepared_simt(const LaunchParams& p, int grid, size_t smem, cudaStream_t stream);
-size_t prepared_mma_size();
+void* prepared_mma_new();
+void prepared_mma_delete(void* prepared);
 int prepare_accumulate_mma(const LaunchParams& p, const DeviceInfo& dev, void* prepared);
 int launch_prepared_mma(const void* prepared, cudaStream_t stream);
 bool mma_supported(const LayerParams& l);

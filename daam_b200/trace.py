@@ -151,7 +151,7 @@ class DiffusionHeatMapHooker(AggregateHooker):
             if not slab.touched:
                 heat_maps.mark_live(slab)
         else:
-            st = self._describe(layer_idx, factor, q, k, heads, scale, pos)
+            st, q, k = self._describe(layer_idx, factor, q, k, heads, scale, pos)    # (q, k: contiguous copies if it made any)
             slab = st[4]
         if self.launch == 'layer':
             if torch.cuda.is_current_stream_capturing():
@@ -164,7 +164,8 @@ class DiffusionHeatMapHooker(AggregateHooker):
         self._n_pending = pos + 1
 
     def _describe(self, layer_idx: int, factor: int, q: torch.Tensor, k: torch.Tensor, heads: int, scale: float, pos: int):
-        """Slow path of :meth:`_enqueue`: (re)build the layer's slab and descriptor and cache them."""
+        """Slow path of :meth:`_enqueue`: (re)build the layer's slab and descriptor and cache them. Returns the state and
+        the tensors the descriptor points into (the caller keeps those alive, not the originals)."""
         if not q.is_cuda:
             raise RuntimeError('daam_b200 traces pipelines that live on a CUDA device only (there is no CPU '
                                'fallback)')
@@ -207,7 +208,7 @@ class DiffusionHeatMapHooker(AggregateHooker):
         state = (shape_key, q.dtype, pos, slot, slab, desc.q - q.data_ptr(), desc.k - k.data_ptr(), q.get_device(), own)
         self._layer_state[layer_idx] = state
         self._device = q.device
-        return state
+        return state, q, k
 
     def _launch_now(self, own, device):
         """``launch='layer'``: the layer's kernel right away on the current stream (the producer of Q/K may be the

@@ -321,3 +321,29 @@ def test_several_images_per_prompt_enumerate_images_x_heads_like_the_reference()
         assert len(got) == n * 25
         out = tc.compute_global_heat_map().heat_maps                 # mean over images x heads x layers, one prompt
         assert out.shape == (4, 64, 64)
+
+
+@pytest.mark.parametrize('launch', ['step', 'layer'])
+def test_projections_with_a_strided_channel_axis_are_copied_and_kept_alive(launch):
+    """to_q / to_k outputs whose channel axis is not contiguous (stride(-1) != 1) cannot be described to the kernel in
+    place: the tracer works on contiguous copies and must keep THOSE alive until the step's launch has run."""
+    from tests.util import assert_elementwise
+    pipe = make_pipeline(TINY_SPEC, dtype=torch.float16, device=DEV, seed=1)
+    g = torch.Generator().manual_seed(7)
+    hw, heads, d = 1024, 2, 64
+    with trace(pipe, launch=launch) as tc:
+        ref = torch.zeros(heads, 77, hw)
+        for step in range(3):
+            q = torch.randn(2, heads * d, hw, generator=g).half().to(DEV).transpose(1, 2)      # [2, hw, C], stride(-1) = hw
+            k = torch.randn(2, heads * d, 77, generator=g).half().to(DEV).transpose(1, 2)
+            assert q.stride(-1) != 1
+            tc._enqueue(3, 2, q, k, heads, d ** -0.5)
+            ref += O.port_layer_step(q.float().cpu(), k.float().cpu(), heads, d ** -0.5).reshape(heads, 77, hw)
+            del q, k
+            torch.empty(8 << 20, device=DEV).fill_(1.0)          # churn the allocator: freed copies would be overwritten
+            tc.flush()
+        tc.synchronize()
+        torch.cuda.synchronize()
+        got = {key: v for key, v in tc.all_heat_maps}
+        for head in range(heads):
+            assert_elementwise(got[(2, 3, head)], ref[head].reshape(77, 32, 32), 1e-4, 3e-5, f'head {head}')
