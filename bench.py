@@ -368,7 +368,7 @@ def leg_hook_overhead(args, spec, dtype, windows):
         base = run(n)
         res = {}
         mid = args.workload == 'sdxl70'
-        for mode in ('step', 'layer'):
+        for mode in ('step', 'overlap', 'layer'):
             with trace(pipe, launch=mode, locate_middle_block=mid) as tc:
                 run(5)
                 res[mode] = run(n)
@@ -417,6 +417,7 @@ def leg_hook_overhead(args, spec, dtype, windows):
             'hooked_ms_per_step': round(res['step'], 4), 'overhead_ms_per_step': round(res['step'] - base, 4),
             'overhead_pct': round(100 * (res['step'] - base) / base, 3),
             'hooked_layer_mode_ms_per_step': round(res['layer'], 4),
+            'hooked_overlap_mode_ms_per_step': round(res['overlap'], 4),
             'model': f'{spec.name} full-body synthetic UNet, CFG batch 2, {str(dtype).split(".")[-1]}, median of {n} forwards'}
 
 

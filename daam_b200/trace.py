@@ -8,8 +8,9 @@ exceptions; what differs is what runs underneath.
   heat-map side of the call -- ``get_attention_scores`` + ``_unravel_attn`` + the per-head ``update`` loop (trace.py:
   276, 219-244, 293-294) -- is one fused CUDA kernel (``daam_accumulate``) reading the Q/K projections in place.
 * Kernel work is queued per denoising step and issued as ONE persistent launch covering every traced layer of the step
-  (``launch='step'``, default) on a side stream, so it overlaps the next step's UNet forward; ``launch='layer'`` issues it
-  immediately per layer on the current stream.
+  at the end of the UNet forward, on the forward's own stream (``launch='step'``, default: one CUDA call per step, the
+  kernel is 0.2 % of a step) or on a side stream so that it also overlaps the next step's first kernels
+  (``launch='overlap'``: four CUDA calls per step); ``launch='layer'`` issues it immediately per layer.
 * ``compute_global_heat_map`` (trace.py:83-132) keeps the Python-side key filter and error messages and runs the
   bicubic-upsample / clamp / mean / normalise reduction as one kernel (``daam_finalize``).
 
@@ -37,7 +38,7 @@ __all__ = ['trace', 'DiffusionHeatMapHooker', 'GlobalHeatMap', 'UNetCrossAttenti
 class DiffusionHeatMapHooker(AggregateHooker):
     """Context manager that traces every located cross-attention layer of ``pipeline.unet`` (trace.py:22-59).
 
-    Extra keyword-only options (not in the reference): ``launch`` ('step' | 'layer', see module docstring),
+    Extra keyword-only options (not in the reference): ``launch`` ('step' | 'overlap' | 'layer', see module docstring),
     ``batch_prompts`` (accept several prompts per generation: N independent single-prompt traces sharing each launch;
     the reference rejects this, trace.py:172-173) and ``locate_middle_block`` (also locate the mid block without
     enabling save/load of heads -- BASELINE config 5 "all 16+70 layers").
@@ -46,8 +47,8 @@ class DiffusionHeatMapHooker(AggregateHooker):
     def __init__(self, pipeline, low_memory: bool = False, load_heads: bool = False, save_heads: bool = False,
                  data_dir: str = None, *, launch: str = 'step', batch_prompts: bool = False,
                  locate_middle_block: bool = False, kernel_flags: int = _native.ACC_AUTO):
-        if launch not in ('step', 'layer'):
-            raise ValueError("launch must be 'step' or 'layer'")
+        if launch not in ('step', 'overlap', 'layer'):
+            raise ValueError("launch must be 'step', 'overlap' or 'layer'")
         _native.load()   # fail here, loudly, if the CUDA library is missing
         self.all_heat_maps = RawHeatMapCollection()
         side = pipeline.unet.config.sample_size * pipeline.vae_scale_factor
@@ -112,7 +113,7 @@ class DiffusionHeatMapHooker(AggregateHooker):
         super()._hook_impl()
         unet = self.pipe.unet
         self._forward_hook = None
-        if self.launch == 'step' and hasattr(unet, 'register_forward_hook'):
+        if self.launch != 'layer' and hasattr(unet, 'register_forward_hook'):
             # end of every UNet forward = end of the step's layer calls: issue the step launch right away
             self._forward_hook = unet.register_forward_hook(lambda *_: self.flush())
 
@@ -141,7 +142,7 @@ class DiffusionHeatMapHooker(AggregateHooker):
         if heat_maps.epoch != self._epoch_seen:            # a slab was (re)allocated: cached descriptors may be stale
             self._layer_state.clear()
             self._epoch_seen = heat_maps.epoch
-        pos = self._n_pending if self.launch == 'step' else 0
+        pos = self._n_pending if self.launch != 'layer' else 0
         st = self._layer_state.get(layer_idx)
         if st is not None and q.shape == st[0] and q.dtype is st[1] and st[2] == pos and q.is_contiguous() \
                 and k.is_contiguous() and q.get_device() == st[7]:
@@ -190,7 +191,7 @@ class DiffusionHeatMapHooker(AggregateHooker):
         slab = self.all_heat_maps.slab_for(layer_idx, factor, n_real, images * n_heads, side, side, q.device, head0)
         self._epoch_seen = self.all_heat_maps.epoch        # (this call may have bumped it; the other layers' slabs stand)
         desc = ops.make_layer_desc(q, k, slab.acc.view(n_samples, n_heads, slab.acc.shape[2], hw), heads, scale)
-        if self.launch == 'step':
+        if self.launch != 'layer':
             if pos >= len(self._slots):                    # grow the step array (SDXL: 70 layers)
                 grown = _native.PackedLayers([_native.DaamLayer()] * (2 * len(self._slots)))
                 for i in range(pos):
@@ -237,7 +238,7 @@ class DiffusionHeatMapHooker(AggregateHooker):
         ops.accumulate_probs(probs, slab.acc)
 
     def flush(self):
-        """Issue the queued layer calls as one persistent launch (per pack of 32 layers) on the side stream."""
+        """Issue the queued layer calls as one persistent launch (per pack of 32 layers)."""
         n = self._n_pending
         if n == 0:
             return
@@ -252,13 +253,18 @@ class DiffusionHeatMapHooker(AggregateHooker):
         if switch:
             torch.cuda.set_device(index)
         try:
-            if torch.cuda.is_current_stream_capturing():
-                # CUDA-graph capture of the UNet step: the launch becomes a node of the captured stream itself (its
-                # predecessor there is the tail of the UNet forward, never a producer of the queued Q/K: EARLY_LOADS holds)
+            capturing = torch.cuda.is_current_stream_capturing()
+            if capturing:
+                # CUDA-graph capture of the UNet step: the launch becomes a node of the captured stream; replays bypass the
+                # Python hook, so the layers of this launch stay live across per-generation resets
                 step = self._step_id
                 for layer_idx, st in self._layer_state.items():
                     if self._queued.get(layer_idx) == step:
                         st[4].captured = True
+            if capturing or self.launch == 'step':
+                # On the forward's own stream: the predecessor there is the tail of the UNet forward, never a producer of
+                # the queued Q/K, so only the accumulator updates have to wait for it (EARLY_LOADS). Stream order also
+                # makes it safe to drop the projections right after the launch.
                 _native.accumulate(packed, current, flags)
             else:
                 side = self._side_stream(device)
@@ -268,8 +274,7 @@ class DiffusionHeatMapHooker(AggregateHooker):
                     self._parked = []
                 # One foreign call: event on the current stream (Q/K were produced there) -> the side stream waits ->
                 # launch -> `done` event. The side stream carries nothing but these launches and the projections are
-                # complete before the previous one could have started, so only the accumulator updates need to wait
-                # for it (EARLY_LOADS).
+                # complete before the previous one could have started (EARLY_LOADS holds here too).
                 self._launcher.launch(packed, flags, current, side.cuda_stream)
                 self._parked.append(self._refs)                # alive until a later idle() / join says the kernel has run
                 self._dirty = True

@@ -46,7 +46,7 @@ class Recorder:
 
 
 @pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.bfloat16, 4e-4), (torch.float16, 4e-4)])
-@pytest.mark.parametrize('launch', ['step', 'layer'])
+@pytest.mark.parametrize('launch', ['step', 'overlap', 'layer'])
 def test_pipeline_parity_with_oracle_on_identical_qk(dtype, tol, launch):
     pipe = make_pipeline(TINY_SPEC, dtype=dtype, device=DEV, seed=3)
     with trace(pipe, launch=launch) as tc:
@@ -153,7 +153,7 @@ def test_low_memory_and_mid_block_options():
         assert tc._gen_idx == 16
 
 
-@pytest.mark.parametrize('launch', ['step', 'layer'])
+@pytest.mark.parametrize('launch', ['step', 'overlap', 'layer'])
 def test_cuda_graph_replay_traces_like_eager(launch):
     """The tracer's kernels become nodes of a captured UNet step: graph replays must accumulate exactly like eager."""
     prompt = 'a dog chasing a red ball'
@@ -323,7 +323,7 @@ def test_several_images_per_prompt_enumerate_images_x_heads_like_the_reference()
         assert out.shape == (4, 64, 64)
 
 
-@pytest.mark.parametrize('launch', ['step', 'layer'])
+@pytest.mark.parametrize('launch', ['step', 'overlap', 'layer'])
 def test_projections_with_a_strided_channel_axis_are_copied_and_kept_alive(launch):
     """to_q / to_k outputs whose channel axis is not contiguous (stride(-1) != 1) cannot be described to the kernel in
     place: the tracer works on contiguous copies and must keep THOSE alive until the step's launch has run."""

@@ -4,6 +4,7 @@ TAG=${1:-r02z}
 mkdir -p gpurun_out
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee gpurun_out/${TAG}_pytest.txt
+echo "== hook breakdown"; timeout 300 python tools/profile_hook.py 2>&1 | tail -32
 echo "== finalize"; timeout 300 python tools/microbench_finalize.py --workload sd21 2>&1 | tail -1
 timeout 300 python tools/microbench_finalize.py --workload sdxl70 2>&1 | tail -1
 echo "== ncu finalize"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:finalize_fast -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_finalize \

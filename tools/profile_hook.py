@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Where the eager hook overhead goes (run on the GPU box): wall time of un-hooked vs hooked forwards of the full-cost
-SD-2.1 UNet, with the host time spent inside the tracer's _enqueue / flush, and the same with the kernel launch stubbed
-out (host bookkeeping only) or the whole flush stubbed out."""
+SD-2.1 UNet, with the host time spent inside the tracer's _enqueue / flush, for the default step launch (on the forward's
+stream), the side-stream variant (launch='overlap'), and with the whole flush stubbed out."""
 import json
 import os
 import sys
@@ -37,8 +37,8 @@ def main():
     with torch.no_grad():
         run(5)
         res['unhooked_issue_ms'], res['unhooked_wall_ms'] = run(n)
-        for mode in ('full', 'no_launch', 'no_flush'):
-            with trace(pipe) as tc:
+        for mode in ('step', 'overlap', 'no_flush'):
+            with trace(pipe, launch='overlap' if mode == 'overlap' else 'step') as tc:
                 acc = {'enqueue': 0.0, 'flush': 0.0, 'n_enq': 0, 'n_flush': 0}
                 enq, fl = tc._enqueue, tc.flush
 
@@ -62,12 +62,6 @@ def main():
 
                 tc._enqueue, tc.flush = enqueue, flush
                 run(5)
-                if mode == 'no_launch':
-                    class Stub:
-                        def idle(self): return True
-                        def launch(self, *a): pass
-                        def join(self, *a): pass
-                    tc._launcher = Stub()
                 acc.update(enqueue=0.0, flush=0.0, n_enq=0, n_flush=0)
                 issue, wall = run(n)
                 res[mode] = {'issue_ms': round(issue, 4), 'wall_ms': round(wall, 4),
