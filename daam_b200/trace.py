@@ -272,6 +272,9 @@ class DiffusionHeatMapHooker(AggregateHooker):
                     self._launcher = _native.SideLauncher()
                 if self._parked and self._launcher.idle():     # the previous launches have run: drop their projections
                     self._parked = []
+                elif len(self._parked) >= 8:                   # the host runs many steps ahead of the device: do not let
+                    side.synchronize()                         # parked projections pile up (they pin allocator blocks)
+                    self._parked = []
                 # One foreign call: event on the current stream (Q/K were produced there) -> the side stream waits ->
                 # launch -> `done` event. The side stream carries nothing but these launches and the projections are
                 # complete before the previous one could have started (EARLY_LOADS holds here too).
