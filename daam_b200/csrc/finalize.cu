@@ -553,12 +553,9 @@ extern "C" int daam_finalize(const daam_key_group* groups, int32_t n_groups, int
   }
   if (fast) {
     // 8-row bands unless that leaves the machine under-filled (< 2 CTAs per SM) or a band's source pixels of the
-    // factor-2 class would exceed one CTA's 256 threads (x > 128)
+    // factor-2 class would exceed one CTA's 256 threads (x > 128); forcing either height measured the same within 1 %
+    // for the 175-key SD-2.1 case
     cls.band_rows = ((x / 8) * n_rows >= 2 * dev.sm_count && x <= 128) ? 8 : 4;
-    if (const char* e = getenv("DAAM_EXP_FINALIZE_BAND")) {   // EXPERIMENT: force the band height
-      if (e[0] == '8' && x <= 128) cls.band_rows = 8;
-      if (e[0] == '4') cls.band_rows = 4;
-    }
     int next = 0;
     for (int c = 0; c < cls.n; ++c) {                   // keys[] of the kernel: class by class, groups in call order
       cls.key_begin[c] = next;
