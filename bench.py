@@ -350,7 +350,8 @@ def leg_hook_overhead(args, spec, dtype, windows):
     emb = torch.randn(2, spec_.tokens, spec_.cross_attention_dim, device='cuda', dtype=dtype)
     t_dev = torch.full((1,), 500.0, device='cuda')
 
-    def run(k):
+    def forwards(k):
+        """Per-forward device times (CUDA events) of k forwards."""
         times = []
         for i in range(k):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -359,25 +360,35 @@ def leg_hook_overhead(args, spec, dtype, windows):
             b.record()
             times.append((a, b))
         torch.cuda.synchronize()
-        ts = sorted(a.elapsed_time(b) for a, b in times)
+        return [a.elapsed_time(b) for a, b in times]
+
+    def median(ts):
+        ts = sorted(ts)
         return ts[len(ts) // 2]
 
+    def run(k):
+        return median(forwards(k))
+
     t0 = time.time()
+    rounds, per_round = 4, 10
     with torch.no_grad():
         run(5)
-        base = run(n)
-        res = {}
         mid = args.workload == 'sdxl70'
-        for mode in ('step', 'overlap', 'layer'):
+        # un-hooked and hooked forwards in alternating rounds (host jitter and clock drift hit both sides alike); the
+        # figure is the difference of the medians over all forwards of each side
+        unhooked_ts, hooked_ts = [], []
+        for _ in range(rounds):
+            unhooked_ts += forwards(per_round)
+            with trace(pipe, launch='step', locate_middle_block=mid) as tc:
+                run(3)
+                hooked_ts += forwards(per_round)
+                tc.synchronize()
+        base, res = median(unhooked_ts), {'step': median(hooked_ts)}
+        for mode in ('overlap', 'layer'):
             with trace(pipe, launch=mode, locate_middle_block=mid) as tc:
                 run(5)
                 res[mode] = run(n)
                 tc.synchronize()
-        base2 = run(n)
-        with trace(pipe, launch='step', locate_middle_block=mid) as tc:       # second hooked sample after the second un-hooked one: both
-            run(5)                                    # sides get the best of two interleaved medians (host jitter)
-            res['step'] = min(res['step'], run(n))
-            tc.synchronize()
         # the same comparison with the forward replayed from a CUDA graph (no host launch cost on either side)
         def graphed():
             g = torch.cuda.CUDAGraph()
@@ -406,7 +417,6 @@ def leg_hook_overhead(args, spec, dtype, windows):
         except Exception as e:
             gres['error'] = repr(e)
     windows.append((t0, time.time()))
-    base = min(base, base2)
     graph = {}
     if 'hooked' in gres:
         graph = {'graph_unhooked_ms_per_step': round(gres['unhooked'], 4), 'graph_hooked_ms_per_step': round(gres['hooked'], 4),
@@ -418,7 +428,8 @@ def leg_hook_overhead(args, spec, dtype, windows):
             'overhead_pct': round(100 * (res['step'] - base) / base, 3),
             'hooked_layer_mode_ms_per_step': round(res['layer'], 4),
             'hooked_overlap_mode_ms_per_step': round(res['overlap'], 4),
-            'model': f'{spec.name} full-body synthetic UNet, CFG batch 2, {str(dtype).split(".")[-1]}, median of {n} forwards'}
+            'model': f'{spec.name} full-body synthetic UNet, CFG batch 2, {str(dtype).split(".")[-1]}, medians of '
+                     f'{rounds * per_round} un-hooked and {rounds * per_round} hooked forwards in {rounds} alternating rounds'}
 
 
 def pick_cpu_threads(step_fn, budget_s=20.0):
