@@ -90,9 +90,11 @@ typedef struct daam_layer {
 int daam_accumulate(const daam_layer* layers, int32_t n_layers, uint32_t flags, void* stream);
 
 /*
- * The tracer's step launch (daam_b200/trace.py flush): the reference's hook does its heat-map work inline on the
- * pipeline's stream (daam/trace.py:276-294); here one launch per denoising step runs on a SIDE stream so that it overlaps
- * the next step's UNet forward. This helper does the stream plumbing of that launch in one foreign call:
+ * The tracer's optional side-stream launch (daam_b200/trace.py flush, launch='overlap'): the reference's hook does its
+ * heat-map work inline on the pipeline's stream (daam/trace.py:276-294), and so does the tracer by default (one
+ * daam_accumulate per denoising step on the forward's own stream). With launch='overlap' that one launch runs on a
+ * side stream so that it also overlaps the next step's first kernels; this helper does the stream plumbing in one
+ * foreign call:
  *   launch: record an event on `producer_stream` (where to_q / to_k ran), make `side_stream` wait for it,
  *           daam_accumulate(layers, n_layers, flags, side_stream), record the launcher's `done` event on side_stream;
  *   join:   make `stream` wait for the last launch (before anything reads the accumulators or frees the projections);
