@@ -156,11 +156,13 @@ int build_plan(const daam_layer* layers, int n_layers, uint32_t flags, const Dev
     const int which = use_mma ? (L.dtype == DAAM_F32 ? 1 : 0) : 2;
     LaunchParams& p = packs[which];
     L.tile_begin = p.total_tiles;
-    // Cost of a tile relative to the launch's other layers. Every 64-wide K chunk is one load -> (convert ->) MMA
-    // round: in the fp32 split form that chain is the tile's cost; in the 16-bit form the chunks are cheap next to the
-    // tile's fixed 77 x 128 accumulator update (two units).
+    // Cost of a tile relative to the launch's other layers, measured on SD-1.5's 40 / 80 / 160 head dims
+    // (profiles/r02_microbench_experiments.json, "weight A+B*chunks"): every 64-wide K chunk is one load -> (convert ->)
+    // MMA round through the two-stage ring. In the fp32 split form that chain is the whole cost of a tile (weight =
+    // chunks; any constant term measured slower); in the 16-bit form 1 + 4 * chunks did best at 1-2 prompts per launch
+    // (0.80 vs 0.73 for 2 + chunks) and the same as every other model at 8.
     const int n_chunks = (L.head_dim + 63) / 64;
-    L.weight = which == 1 ? n_chunks : 2 + n_chunks;
+    L.weight = which == 1 ? n_chunks : 1 + 4 * n_chunks;
     L.weight_begin = p.total_weight;
     p.layer[p.n_layers++] = L;
     p.total_tiles += L.tiles_per_head * L.heads * L.n_prompts;
