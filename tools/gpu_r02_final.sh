@@ -8,8 +8,7 @@ echo "== hook breakdown"; timeout 300 python tools/profile_hook.py 2>&1 | tail -
 echo "== finalize"; timeout 300 python tools/microbench_finalize.py --workload sd21 2>&1 | tail -1
 timeout 300 python tools/microbench_finalize.py --workload sdxl70 2>&1 | tail -1
 echo "== ncu finalize"; timeout 600 ncu --set full --clock-control none --import-source on -k regex:finalize_fast -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_finalize \
-  python tools/microbench_finalize.py --workload sd21 > gpurun_out/${TAG}_ncu_fin.log 2>&1; tail -1 gpurun_out/${TAG}_ncu_fin.log | cut -c1-200
-cp gpurun_out/microbench_finalize_sd21.json gpurun_out/${TAG}_microbench_finalize_sd21.json 2>/dev/null
+  python tools/microbench_finalize.py --no-save --workload sd21 > gpurun_out/${TAG}_ncu_fin.log 2>&1; tail -1 gpurun_out/${TAG}_ncu_fin.log | cut -c1-200
 echo "== microbench"; timeout 300 python tools/microbench.py --workload sd21 --dtypes bf16 fp32 --prompts 1 8 --variants mma-red-early mma-red mma-red-nopdl 2>&1 | grep -v "per_layer\": true" | tail -12
 timeout 300 python tools/microbench.py --workload sd15 --dtypes fp16 fp32 --prompts 1 8 --variants mma-red-early 2>&1 | grep -v "per_layer\": true" | tail -4
 B="timeout 900 python bench.py --warmup 5"

@@ -34,6 +34,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--workload', default='sd21')
     ap.add_argument('--rows', type=int, default=16)
+    ap.add_argument('--no-save', action='store_true', help='do not write gpurun_out/microbench_finalize_*.json (runs under ncu)')
     args = ap.parse_args()
     layers = traced_layers(args.workload)
     x = 64
@@ -85,6 +86,8 @@ def main():
     res['expand_words_device_us'] = round(timed(lambda i: ghm.expand_words(words, img, to_cpu=False), 20, gate=False), 2)
     res['n_words'] = len(words)
     print(json.dumps(res))
+    if args.no_save:
+        return
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', f'microbench_finalize_{args.workload}.json'), 'w') as f:
         json.dump(res, f, indent=1)
