@@ -11,7 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from daam_b200 import _native, trace  # noqa: E402
+from daam_b200 import trace  # noqa: E402
 from daam_b200.testing.synthetic import SD21_SPEC, make_pipeline  # noqa: E402
 
 
