@@ -37,7 +37,7 @@ def main():
     ap.add_argument('--no-save', action='store_true', help='do not write gpurun_out/microbench_finalize_*.json (runs under ncu)')
     args = ap.parse_args()
     layers = traced_layers(args.workload)
-    x = 64
+    x = int(max(hw for hw, _, _ in layers) ** 0.5)        # 64, or 96 for the 768-pixel geometry
     slab_bytes = sum(h * 77 * hw * 4 for hw, h, _ in layers)
     n_sets = max(2, -(-int(400e6) // slab_bytes))
     sets = []
